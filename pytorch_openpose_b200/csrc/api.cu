@@ -1,0 +1,732 @@
+// extern "C" surface of libopenpose_b200.so (include/openpose_b200.h) and the per-frame pipelines behind
+// Body.__call__ (src/body.py:24-212) and Hand.__call__ (src/hand.py:25-75).
+#include "net.cuh"
+#include <cstdlib>
+#include <cstring>
+#include <algorithm>
+
+namespace opb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& m) { g_last_error = m; }
+
+template <typename F>
+static int guarded(F&& f) {
+    try {
+        f();
+        return OPB_OK;
+    } catch (const Error& e) {
+        set_last_error(e.what());
+        return e.code;
+    } catch (const std::exception& e) {
+        set_last_error(e.what());
+        return OPB_ERR_INVALID;
+    }
+}
+
+struct ScaleDims {
+    double mult;
+    int h, w, hp, wp, ho, wo;
+};
+static ScaleDims scale_dims(int H, int W, double scale) {
+    OPB_REQUIRE(H > 0 && W > 0, "empty image (the reference divides by oriImg.shape[0], src/body.py:32)");
+    ScaleDims d;
+    d.mult = scale * 368.0 / (double)H;                 // x * boxsize / oriImg.shape[0], src/body.py:32
+    d.h = resize_dsize(H, d.mult);
+    d.w = resize_dsize(W, d.mult);
+    OPB_REQUIRE(d.h > 0 && d.w > 0, "scaled image is empty");
+    d.hp = (d.h + 7) / 8 * 8;
+    d.wp = (d.w + 7) / 8 * 8;
+    d.ho = d.hp / 8;
+    d.wo = d.wp / 8;
+    return d;
+}
+
+// fixed-point (11-bit) tap tables of cv2's uint8 cubic resize
+struct U8Taps {
+    int *xf, *yf;
+    short *xc, *yc;
+};
+static U8Taps make_u8_taps(DevPool& pool, int H, int W, const ScaleDims& d) {
+    auto conv = [&](const CubicTaps& t, std::vector<short>& out) {
+        out.resize(t.coef.size());
+        for (size_t i = 0; i < t.coef.size(); ++i) {
+            long v = lrintf(t.coef[i] * 2048.0f);       // saturate_cast<short>(coef * INTER_RESIZE_COEF_SCALE)
+            out[i] = (short)std::max(-32768l, std::min(32767l, v));
+        }
+    };
+    const CubicTaps tx = cubic_taps(W, d.w, 1.0 / d.mult), ty = cubic_taps(H, d.h, 1.0 / d.mult);
+    std::vector<short> sx, sy;
+    conv(tx, sx);
+    conv(ty, sy);
+    U8Taps u;
+    u.xf = pool.upload(tx.first);
+    u.yf = pool.upload(ty.first);
+    u.xc = pool.upload(sx);
+    u.yc = pool.upload(sy);
+    return u;
+}
+
+struct UpTables {
+    int *xf, *yf;
+    float *xw, *yw;
+};
+static UpTables make_up_tables(DevPool& pool, int H, int W, const ScaleDims& d) {
+    std::vector<int> fx, fy;
+    std::vector<float> wx, wy;
+    composite_taps(d.wo, d.w, W, fx, wx);
+    composite_taps(d.ho, d.h, H, fy, wy);
+    UpTables t;
+    t.xf = pool.upload(fx);
+    t.yf = pool.upload(fy);
+    t.xw = pool.upload(wx);
+    t.yw = pool.upload(wy);
+    return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame plans
+// ------------------------------------------------------------------------------------------------
+struct FrameKey {
+    int n, H, W;
+    std::vector<double> scales;
+    bool operator<(const FrameKey& o) const {
+        if (n != o.n) return n < o.n;
+        if (H != o.H) return H < o.H;
+        if (W != o.W) return W < o.W;
+        return scales < o.scales;
+    }
+};
+
+struct FramePlan {
+    DevPool pool;
+    FrameKey key;
+    std::vector<ScaleDims> dims;
+    std::vector<U8Taps> u8taps;
+    std::vector<UpTables> uptabs;
+    std::unique_ptr<NetPlan> net;
+    uint8_t* d_img = nullptr;
+    float* up_scratch = nullptr;
+    float* heat_avg = nullptr;      // body: (19,H,W); hand: (n*22,H,W)
+    float* paf_avg = nullptr;       // body: (38,H,W)
+    // body post-processing
+    PeakBuffers pb{};
+    int* part_count = nullptr;
+    LimbBuffers lb{};
+    int* order = nullptr;
+    unsigned char* used = nullptr;
+    // hand post-processing
+    HandBuffers hb{};
+    int launches_per_frame = 0;
+};
+
+constexpr int kPeakCapacity = 16384;
+constexpr int kPairCapacity = 16384;
+constexpr int kConnCapacity = 2048;
+constexpr int kSubsetCapacity = 1024;
+constexpr int kEagerCand = 2048;      // rows copied to the host before the counts are known
+constexpr int kEagerSubset = 128;
+
+static void alloc_body_post(DevPool& pool, FramePlan& fp, int peak_cap, int pair_cap, int conn_cap, int subset_cap) {
+    fp.pb.capacity = peak_cap;
+    fp.pb.keys = pool.alloc_t<unsigned long long>(peak_cap);
+    fp.pb.scores = pool.alloc_t<float>(peak_cap);
+    fp.pb.count = pool.alloc_t<int>(1, true);
+    fp.pb.candidates = pool.alloc_t<double>((size_t)peak_cap * 4, true);
+    fp.pb.part_begin = pool.alloc_t<int>(19, true);
+    fp.part_count = pool.alloc_t<int>(18, true);
+    fp.lb.pair_capacity = pair_cap;
+    fp.lb.conn_capacity = conn_cap;
+    fp.lb.subset_capacity = subset_cap;
+    fp.lb.cand_score = pool.alloc_t<double>((size_t)19 * pair_cap);
+    fp.lb.cand_ij = pool.alloc_t<int>((size_t)19 * pair_cap * 2);
+    fp.lb.cand_count = pool.alloc_t<int>(19, true);
+    fp.lb.conn = pool.alloc_t<double>((size_t)19 * conn_cap * 5, true);
+    fp.lb.conn_count = pool.alloc_t<int>(19, true);
+    fp.lb.subset = pool.alloc_t<double>((size_t)subset_cap * 20, true);
+    fp.lb.subset_count = pool.alloc_t<int>(1, true);
+    fp.lb.status = pool.alloc_t<int>(4, true);
+    fp.order = pool.alloc_t<int>((size_t)19 * pair_cap);
+    fp.used = pool.alloc_t<unsigned char>((size_t)19 * 2 * peak_cap);
+}
+
+}  // namespace opb
+
+using namespace opb;
+
+struct HostResults {                 // pinned
+    int counts[32];                  // [0] peaks appended, [1..19] part_begin, [20] subset rows, [21..24] status
+    double cand[kEagerCand * 4];
+    double subset[kEagerSubset * 20];
+    double hand_peaks[1];            // flexible tail (allocated to fit)
+};
+
+struct opb_session {
+    opb_net* net = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    std::map<FrameKey, std::unique_ptr<FramePlan>> plans;
+    FramePlan* active = nullptr;
+    HostResults* host = nullptr;     // pinned
+    size_t host_bytes = 0;
+    uint8_t* staging = nullptr;      // pinned image staging
+    size_t staging_bytes = 0;
+    std::vector<double> cand_all, subset_all;   // filled by wait() when the eager copy was too small
+    int n_cand = 0, n_subset = 0, status = 0;
+    int hand_crops = 0;
+    // stage-level net plans (opb_net_forward)
+    std::map<std::vector<NetShape>, std::unique_ptr<NetPlan>> net_plans;
+    ~opb_session() {
+        plans.clear();
+        net_plans.clear();
+        if (host) cudaFreeHost(host);
+        if (staging) cudaFreeHost(staging);
+        if (done) cudaEventDestroy(done);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace opb {
+
+static void ensure_host(opb_session* s, size_t hand_doubles) {
+    const size_t need = sizeof(HostResults) + hand_doubles * sizeof(double);
+    if (s->host_bytes >= need) return;
+    if (s->host) cudaFreeHost(s->host);
+    OPB_CUDA(cudaMallocHost((void**)&s->host, need));
+    s->host_bytes = need;
+}
+static void ensure_staging(opb_session* s, size_t bytes) {
+    if (s->staging_bytes >= bytes) return;
+    if (s->staging) cudaFreeHost(s->staging);
+    OPB_CUDA(cudaMallocHost((void**)&s->staging, bytes));
+    s->staging_bytes = bytes;
+}
+
+static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* scales, int n_scales) {
+    OPB_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "scale_search must hold 1..8 entries");
+    FrameKey key{n, H, W, std::vector<double>(scales, scales + n_scales)};
+    auto it = s->plans.find(key);
+    if (it != s->plans.end()) return it->second.get();
+    OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+    auto fp = std::make_unique<FramePlan>();
+    fp->key = key;
+    const bool body = s->net->kind == OPB_NET_BODY;
+    std::vector<NetShape> shapes;
+    size_t scratch = 0;
+    const int C = body ? 57 : 22;
+    for (int i = 0; i < n_scales; ++i) {
+        const ScaleDims d = scale_dims(H, W, scales[i]);
+        fp->dims.push_back(d);
+        fp->u8taps.push_back(make_u8_taps(fp->pool, H, W, d));
+        fp->uptabs.push_back(make_up_tables(fp->pool, H, W, d));
+        shapes.push_back({n, d.hp, d.wp});
+        scratch += (size_t)n * C * d.ho * W;
+    }
+    fp->net = build_net_plan(s->net, shapes);
+    fp->d_img = fp->pool.alloc_t<uint8_t>((size_t)n * H * W * 3);
+    fp->up_scratch = fp->pool.alloc_t<float>(scratch);
+    fp->launches_per_frame = n_scales /*preprocess*/ + fp->net->kernel_launches;
+    if (body) {
+        fp->heat_avg = fp->pool.alloc_t<float>((size_t)19 * H * W);
+        fp->paf_avg = fp->pool.alloc_t<float>((size_t)38 * H * W);
+        alloc_body_post(fp->pool, *fp, kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
+        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + 1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/;
+    } else {
+        fp->heat_avg = fp->pool.alloc_t<float>((size_t)n * 22 * H * W);
+        fp->hb.labels = fp->pool.alloc_t<int>((size_t)n * 21 * H * W);
+        fp->hb.sums = fp->pool.alloc_t<double>((size_t)n * 21 * H * W);
+        fp->hb.peaks = fp->pool.alloc_t<double>((size_t)n * 21 * 3, true);
+        fp->launches_per_frame += (n_scales + 1) + 4;
+    }
+    FramePlan* raw = fp.get();
+    s->plans[key] = std::move(fp);
+    return raw;
+}
+
+static void upload_image(opb_session* s, FramePlan* fp, const uint8_t* img, int where, size_t bytes) {
+    if (where == 1) {                                    // already on the device
+        OPB_CUDA(cudaMemcpyAsync(fp->d_img, img, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    } else if (where == 2) {                             // caller-owned pinned host memory
+        OPB_CUDA(cudaMemcpyAsync(fp->d_img, img, bytes, cudaMemcpyHostToDevice, s->stream));
+    } else {                                             // pageable host memory: stage through pinned
+        ensure_staging(s, bytes);
+        OPB_CUDA(cudaStreamSynchronize(s->stream));      // staging buffer may still feed the previous frame
+        memcpy(s->staging, img, bytes);
+        OPB_CUDA(cudaMemcpyAsync(fp->d_img, s->staging, bytes, cudaMemcpyHostToDevice, s->stream));
+    }
+}
+
+static void run_front(opb_session* s, FramePlan* fp, int n, int H, int W) {
+    cudaStream_t st = s->stream;
+    const int S = (int)fp->dims.size();
+    for (int i = 0; i < S; ++i) {
+        const ScaleDims& d = fp->dims[i];
+        const U8Taps& t = fp->u8taps[i];
+        preprocess_launch_batched(fp->d_img, n, H, W, fp->net->in_u8[i], d.h, d.w, d.hp, d.wp, t.xf, t.xc, t.yf, t.yc, st);
+    }
+    fp->net->run(st);
+}
+
+static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int H, int W, float* out, cudaStream_t st) {
+    UpsampleScale us[kMaxScales];
+    const int S = (int)fp->dims.size();
+    for (int i = 0; i < S; ++i) {
+        us[i].src = paf ? fp->net->out_paf[i] : fp->net->out_heat[i];
+        us[i].ho = fp->dims[i].ho;
+        us[i].wo = fp->dims[i].wo;
+        us[i].cstride = cstride;
+        us[i].x_first = fp->uptabs[i].xf;
+        us[i].x_w = fp->uptabs[i].xw;
+        us[i].y_first = fp->uptabs[i].yf;
+        us[i].y_w = fp->uptabs[i].yw;
+    }
+    upsample_avg_launch2(us, S, n, C, H, W, fp->up_scratch, out, st);
+}
+
+static void body_submit(opb_session* s, const uint8_t* img, int where, int H, int W, const double* scales, int ns) {
+    OPB_REQUIRE(s->net->kind == OPB_NET_BODY, "session was created on a hand network");
+    OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+    FramePlan* fp = get_plan(s, 1, H, W, scales, ns);
+    ensure_host(s, 0);
+    s->active = fp;
+    cudaStream_t st = s->stream;
+    upload_image(s, fp, img, where, (size_t)H * W * 3);
+    run_front(s, fp, 1, H, W);
+    run_upsample(fp, false, 1, 19, 24, H, W, fp->heat_avg, st);
+    run_upsample(fp, true, 1, 38, 40, H, W, fp->paf_avg, st);
+    smooth_nms_launch(fp->heat_avg, H, W, 18, 0.1, fp->pb, nullptr, st);            // thre1, src/body.py:30
+    sort_peaks_launch2(fp->pb, 18, fp->part_count, st);
+    paf_group_launch2(fp->paf_avg, H, W, fp->pb.candidates, fp->pb.part_begin, fp->lb, 0.05, fp->order, fp->used,
+                      fp->pb.capacity, st);                                          // thre2, src/body.py:31
+    HostResults* h = s->host;
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[0], fp->pb.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[1], fp->pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[20], fp->lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[21], fp->lb.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(h->cand, fp->pb.candidates, sizeof(h->cand), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(h->subset, fp->lb.subset, sizeof(h->subset), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaEventRecord(s->done, st));
+    s->net->ctx->launches += fp->launches_per_frame;
+}
+
+static int body_wait(opb_session* s, int* n_cand, int* n_subset) {
+    OPB_REQUIRE(s->active != nullptr, "no frame in flight");
+    FramePlan* fp = s->active;
+    OPB_CUDA(cudaEventSynchronize(s->done));
+    HostResults* h = s->host;
+    const int appended = h->counts[0];
+    const int status = h->counts[21];
+    if (appended > fp->pb.capacity)
+        throw Error(OPB_ERR_CAPACITY, "more than " + std::to_string(fp->pb.capacity) + " heat-map peaks in one frame");
+    if (status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))
+        throw Error(OPB_ERR_CAPACITY, "limb / person buffers overflowed (status " + std::to_string(status) + ")");
+    s->n_cand = h->counts[19];           // part_begin[18] = total
+    s->n_subset = h->counts[20];
+    s->status = status;
+    s->cand_all.clear();
+    s->subset_all.clear();
+    if (s->n_cand > kEagerCand) {
+        s->cand_all.resize((size_t)s->n_cand * 4);
+        OPB_CUDA(cudaMemcpyAsync(s->cand_all.data(), fp->pb.candidates, s->cand_all.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (s->n_subset > kEagerSubset) {
+        s->subset_all.resize((size_t)s->n_subset * 20);
+        OPB_CUDA(cudaMemcpyAsync(s->subset_all.data(), fp->lb.subset, s->subset_all.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+    }
+    if (!s->cand_all.empty() || !s->subset_all.empty()) OPB_CUDA(cudaStreamSynchronize(s->stream));
+    *n_cand = s->n_cand;
+    *n_subset = s->n_subset;
+    if (status & kStIndexError) {
+        set_last_error("list assignment index out of range (three subset rows match one connection, src/body.py:173)");
+        return OPB_ERR_SUBSET_INDEX;
+    }
+    return OPB_OK;
+}
+
+static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, int H, int W, const double* scales, int ns) {
+    OPB_REQUIRE(s->net->kind == OPB_NET_HAND, "session was created on a body network");
+    OPB_REQUIRE(n >= 1 && n <= 1024, "1..1024 crops per batch");
+    OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+    FramePlan* fp = get_plan(s, n, H, W, scales, ns);
+    ensure_host(s, (size_t)n * 63);
+    s->active = fp;
+    s->hand_crops = n;
+    cudaStream_t st = s->stream;
+    upload_image(s, fp, img, where, (size_t)n * H * W * 3);
+    run_front(s, fp, n, H, W);
+    run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);
+    hand_peaks_launch2(fp->heat_avg, n, 22, H, W, 0.03, fp->hb, nullptr, st);        // thre, src/hand.py:31
+    OPB_CUDA(cudaMemcpyAsync(s->host->hand_peaks, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaEventRecord(s->done, st));
+    s->net->ctx->launches += fp->launches_per_frame;
+}
+
+}  // namespace opb
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+int opb_abi_version(void) { return OPB_ABI_VERSION; }
+const char* opb_last_error(void) { return g_last_error.c_str(); }
+
+int opb_context_create(int device, opb_context** out) {
+    return guarded([&] {
+        OPB_REQUIRE(out != nullptr, "null out pointer");
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+            throw Error(OPB_ERR_NO_DEVICE, "no CUDA device visible: libopenpose_b200 has no CPU fallback");
+        OPB_REQUIRE(device >= 0 && device < count, "device index out of range");
+        cudaDeviceProp prop;
+        OPB_CUDA(cudaGetDeviceProperties(&prop, device));
+        if (prop.major != 10)
+            throw Error(OPB_ERR_NO_DEVICE, std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                                               std::to_string(prop.minor) + ": this library is built for sm_100a only");
+        OPB_CUDA(cudaSetDevice(device));
+        auto* c = new opb_context();
+        c->device = device;
+        c->num_sms = prop.multiProcessorCount;
+        OPB_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        *out = c;
+    });
+}
+int opb_context_destroy(opb_context* ctx) {
+    return guarded([&] { delete ctx; });
+}
+int opb_context_synchronize(opb_context* ctx) {
+    return guarded([&] {
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        OPB_CUDA(cudaDeviceSynchronize());
+    });
+}
+int opb_context_launch_count(opb_context* ctx, int64_t* out) {
+    return guarded([&] { *out = ctx->launches; });
+}
+
+int opb_net_create(opb_context* ctx, int kind, opb_net** out) {
+    return guarded([&] {
+        OPB_REQUIRE(ctx && out && (kind == OPB_NET_BODY || kind == OPB_NET_HAND), "bad arguments");
+        auto* n = new opb_net();
+        n->ctx = ctx;
+        n->kind = kind;
+        *out = n;
+    });
+}
+int opb_net_load_layer(opb_net* net, const char* name, const float* weight, const float* bias, int cout, int cin, int k) {
+    return guarded([&] {
+        OPB_REQUIRE(net && name && weight && bias && cout > 0 && cin > 0 && k > 0, "bad arguments");
+        OPB_REQUIRE(!net->finalized, "net already finalized");
+        HostLayer h;
+        h.cout = cout; h.cin = cin; h.k = k;
+        h.w.assign(weight, weight + (size_t)cout * cin * k * k);
+        h.b.assign(bias, bias + cout);
+        net->host[name] = std::move(h);
+    });
+}
+int opb_net_finalize(opb_net* net) {
+    return guarded([&] { finalize_net(net); });
+}
+int opb_net_destroy(opb_net* net) {
+    return guarded([&] { delete net; });
+}
+int opb_net_layer_count(int kind) {
+    if (kind != OPB_NET_BODY && kind != OPB_NET_HAND) return OPB_ERR_INVALID;
+    return (int)layer_specs(kind).size();
+}
+int opb_net_layer_info(int kind, int index, const char** name, int* cout, int* cin, int* k, int* relu) {
+    return guarded([&] {
+        OPB_REQUIRE(kind == OPB_NET_BODY || kind == OPB_NET_HAND, "bad kind");
+        const auto& v = layer_specs(kind);
+        OPB_REQUIRE(index >= 0 && index < (int)v.size(), "layer index out of range");
+        if (name) *name = v[index].name.c_str();
+        if (cout) *cout = v[index].cout;
+        if (cin) *cin = v[index].cin;
+        if (k) *k = v[index].k;
+        if (relu) *relu = v[index].relu ? 1 : 0;
+    });
+}
+
+int opb_session_create(opb_net* net, opb_session** out) {
+    return guarded([&] {
+        OPB_REQUIRE(net && out && net->finalized, "net must be finalized first");
+        OPB_CUDA(cudaSetDevice(net->ctx->device));
+        auto* s = new opb_session();
+        s->net = net;
+        OPB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        OPB_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
+        *out = s;
+    });
+}
+int opb_session_destroy(opb_session* s) {
+    return guarded([&] {
+        if (s) {
+            cudaSetDevice(s->net->ctx->device);
+            cudaStreamSynchronize(s->stream);
+        }
+        delete s;
+    });
+}
+
+int opb_body_submit(opb_session* s, const uint8_t* img, int img_is_device, int H, int W, const double* scales, int ns) {
+    return guarded([&] {
+        OPB_REQUIRE(s && img && scales, "null argument");
+        body_submit(s, img, img_is_device, H, W, scales, ns);
+    });
+}
+int opb_body_wait(opb_session* s, int* n_candidate, int* n_subset) {
+    int rc = OPB_OK;
+    int g = guarded([&] {
+        OPB_REQUIRE(s && n_candidate && n_subset, "null argument");
+        rc = body_wait(s, n_candidate, n_subset);
+    });
+    return g != OPB_OK ? g : rc;
+}
+int opb_body_fetch(opb_session* s, double* candidate, int cand_rows, double* subset, int subset_rows) {
+    return guarded([&] {
+        OPB_REQUIRE(s && s->active, "no finished frame");
+        if (cand_rows < s->n_cand || subset_rows < s->n_subset)
+            throw Error(OPB_ERR_CAPACITY, "fetch buffers smaller than the result");
+        if (s->n_cand) {
+            OPB_REQUIRE(candidate != nullptr, "null candidate buffer");
+            const double* src = s->cand_all.empty() ? s->host->cand : s->cand_all.data();
+            memcpy(candidate, src, (size_t)s->n_cand * 4 * sizeof(double));
+        }
+        if (s->n_subset) {
+            OPB_REQUIRE(subset != nullptr, "null subset buffer");
+            const double* src = s->subset_all.empty() ? s->host->subset : s->subset_all.data();
+            memcpy(subset, src, (size_t)s->n_subset * 20 * sizeof(double));
+        }
+    });
+}
+
+int opb_body_maps(opb_session* s, float* host_heat, float* host_paf) {
+    return guarded([&] {
+        OPB_REQUIRE(s && s->active && s->net->kind == OPB_NET_BODY, "no finished body frame");
+        OPB_CUDA(cudaEventSynchronize(s->done));
+        const size_t px = (size_t)s->active->key.H * s->active->key.W;
+        if (host_heat) OPB_CUDA(cudaMemcpy(host_heat, s->active->heat_avg, px * 19 * 4, cudaMemcpyDeviceToHost));
+        if (host_paf) OPB_CUDA(cudaMemcpy(host_paf, s->active->paf_avg, px * 38 * 4, cudaMemcpyDeviceToHost));
+    });
+}
+int opb_hand_maps(opb_session* s, float* host_heat) {
+    return guarded([&] {
+        OPB_REQUIRE(s && s->active && s->net->kind == OPB_NET_HAND && host_heat, "no finished hand batch");
+        OPB_CUDA(cudaEventSynchronize(s->done));
+        const size_t px = (size_t)s->active->key.H * s->active->key.W;
+        OPB_CUDA(cudaMemcpy(host_heat, s->active->heat_avg, px * 22 * 4 * s->active->key.n, cudaMemcpyDeviceToHost));
+    });
+}
+
+int opb_hand_submit(opb_session* s, const uint8_t* crops, int img_is_device, int n, int H, int W, const double* scales, int ns) {
+    return guarded([&] {
+        OPB_REQUIRE(s && crops && scales, "null argument");
+        hand_submit(s, crops, img_is_device, n, H, W, scales, ns);
+    });
+}
+int opb_hand_wait(opb_session* s, double* peaks) {
+    return guarded([&] {
+        OPB_REQUIRE(s && s->active && peaks, "no frame in flight");
+        OPB_CUDA(cudaEventSynchronize(s->done));
+        memcpy(peaks, s->host->hand_peaks, (size_t)s->hand_crops * 63 * sizeof(double));
+    });
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-level entry points
+// ---------------------------------------------------------------------------------------------
+int opb_scale_dims(int H, int W, double scale, int* h, int* w, int* hp, int* wp) {
+    return guarded([&] {
+        const ScaleDims d = scale_dims(H, W, scale);
+        if (h) *h = d.h;
+        if (w) *w = d.w;
+        if (hp) *hp = d.hp;
+        if (wp) *wp = d.wp;
+    });
+}
+
+int opb_preprocess(opb_context* ctx, const uint8_t* dev_img, int H, int W, double scale, uint8_t* dev_out) {
+    return guarded([&] {
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        const ScaleDims d = scale_dims(H, W, scale);
+        DevPool pool;
+        const U8Taps t = make_u8_taps(pool, H, W, d);
+        preprocess_launch(dev_img, H, W, dev_out, d.h, d.w, d.hp, d.wp, t.xf, t.xc, t.yf, t.yc, ctx->stream);
+        ctx->launches += 1;
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int opb_net_forward(opb_session* s, const uint8_t* dev_in, int n, int hp, int wp, float* dev_paf, float* dev_heat) {
+    return guarded([&] {
+        OPB_REQUIRE(s && dev_in && dev_heat, "null argument");
+        OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+        std::vector<NetShape> shapes{{n, hp, wp}};
+        auto& plan = s->net_plans[shapes];
+        if (!plan) plan = build_net_plan(s->net, shapes);
+        const size_t px = (size_t)n * (hp / 8) * (wp / 8);
+        OPB_CUDA(cudaMemcpyAsync(plan->in_u8[0], dev_in, (size_t)n * hp * wp * 3, cudaMemcpyDeviceToDevice, s->stream));
+        plan->run(s->stream);
+        if (s->net->kind == OPB_NET_BODY) {
+            OPB_REQUIRE(dev_paf != nullptr, "null paf output");
+            OPB_CUDA(cudaMemcpyAsync(dev_paf, plan->out_paf[0], px * 40 * 4, cudaMemcpyDeviceToDevice, s->stream));
+        }
+        OPB_CUDA(cudaMemcpyAsync(dev_heat, plan->out_heat[0], px * 24 * 4, cudaMemcpyDeviceToDevice, s->stream));
+        s->net->ctx->launches += plan->kernel_launches;
+        OPB_CUDA(cudaStreamSynchronize(s->stream));
+    });
+}
+
+int opb_upsample_avg(opb_context* ctx, const float* const* dev_maps, const double* scales, int ns, int C, int cstride,
+                     int H, int W, float* dev_out) {
+    return guarded([&] {
+        OPB_REQUIRE(ns >= 1 && ns <= kMaxScales, "1..8 scales");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool pool;
+        UpsampleScale us[kMaxScales];
+        size_t scratch = 0;
+        for (int i = 0; i < ns; ++i) {
+            const ScaleDims d = scale_dims(H, W, scales[i]);
+            const UpTables t = make_up_tables(pool, H, W, d);
+            us[i] = UpsampleScale{dev_maps[i], d.ho, d.wo, cstride, t.xf, t.xw, t.yf, t.yw};
+            scratch += (size_t)C * d.ho * W;
+        }
+        float* tmp = pool.alloc_t<float>(scratch);
+        upsample_avg_launch2(us, ns, 1, C, H, W, tmp, dev_out, ctx->stream);
+        ctx->launches += ns + 1;
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int opb_find_peaks(opb_context* ctx, const float* dev_heat, int H, int W, double thre1, double* dev_candidates,
+                   int capacity, int* host_part_begin19, int* n) {
+    return guarded([&] {
+        OPB_REQUIRE(capacity > 0 && dev_candidates && host_part_begin19 && n, "bad arguments");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool pool;
+        PeakBuffers pb;
+        pb.capacity = capacity;
+        pb.keys = pool.alloc_t<unsigned long long>(capacity);
+        pb.scores = pool.alloc_t<float>(capacity);
+        pb.count = pool.alloc_t<int>(1, true);
+        pb.candidates = dev_candidates;
+        pb.part_begin = pool.alloc_t<int>(19, true);
+        int* part_count = pool.alloc_t<int>(18, true);
+        smooth_nms_launch(dev_heat, H, W, 18, thre1, pb, nullptr, ctx->stream);
+        sort_peaks_launch2(pb, 18, part_count, ctx->stream);
+        ctx->launches += 3;
+        int appended = 0;
+        OPB_CUDA(cudaMemcpyAsync(&appended, pb.count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaMemcpyAsync(host_part_begin19, pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *n = appended;
+        if (appended > capacity) throw Error(OPB_ERR_CAPACITY, "peak buffer too small");
+    });
+}
+
+int opb_smooth_debug(opb_context* ctx, const float* dev_heat, int parts, int H, int W, double* dev_smoothed) {
+    return guarded([&] {
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool pool;
+        PeakBuffers pb;
+        pb.capacity = 1;
+        pb.keys = pool.alloc_t<unsigned long long>(1);
+        pb.scores = pool.alloc_t<float>(1);
+        pb.count = pool.alloc_t<int>(1, true);
+        pb.candidates = pool.alloc_t<double>(4);
+        pb.part_begin = pool.alloc_t<int>(19, true);
+        smooth_nms_launch(dev_heat, H, W, parts, 1e300, pb, dev_smoothed, ctx->stream);
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int opb_group_limbs(opb_context* ctx, const float* dev_paf, int H, int W, const double* dev_candidates,
+                    const int* host_part_begin19, double thre2, double* host_subset, int subset_capacity, int* n_subset,
+                    double* host_connections, int conn_capacity, int* host_conn_count19) {
+    int rc = OPB_OK;
+    int g = guarded([&] {
+        OPB_REQUIRE(dev_paf && dev_candidates && host_part_begin19 && host_subset && n_subset, "null argument");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool pool;
+        FramePlan fp;
+        const int total = host_part_begin19[18];
+        int max_part = 1;
+        for (int p = 0; p < 18; ++p) max_part = std::max(max_part, host_part_begin19[p + 1] - host_part_begin19[p]);
+        const int conn_cap = conn_capacity > 0 ? conn_capacity : std::max(1, max_part);
+        alloc_body_post(pool, fp, std::max(total, 1), kPairCapacity, conn_cap, std::min(std::max(subset_capacity, 1), 1280));
+        OPB_CUDA(cudaMemcpy(fp.pb.part_begin, host_part_begin19, 19 * sizeof(int), cudaMemcpyHostToDevice));
+        paf_group_launch2(dev_paf, H, W, dev_candidates, fp.pb.part_begin, fp.lb, thre2, fp.order, fp.used,
+                          std::max(total, 1), ctx->stream);
+        ctx->launches += 3;
+        int status[4], count = 0;
+        OPB_CUDA(cudaMemcpyAsync(status, fp.lb.status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaMemcpyAsync(&count, fp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (status[0] & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))
+            throw Error(OPB_ERR_CAPACITY, "limb / person buffers overflowed (status " + std::to_string(status[0]) + ")");
+        *n_subset = count;
+        if (count > subset_capacity) throw Error(OPB_ERR_CAPACITY, "subset buffer too small");
+        if (count) OPB_CUDA(cudaMemcpy(host_subset, fp.lb.subset, (size_t)count * 20 * 8, cudaMemcpyDeviceToHost));
+        if (host_connections && host_conn_count19) {
+            OPB_CUDA(cudaMemcpy(host_conn_count19, fp.lb.conn_count, 19 * sizeof(int), cudaMemcpyDeviceToHost));
+            OPB_CUDA(cudaMemcpy(host_connections, fp.lb.conn, (size_t)19 * conn_cap * 5 * 8, cudaMemcpyDeviceToHost));
+        }
+        if (status[0] & kStIndexError) {
+            set_last_error("list assignment index out of range (src/body.py:173)");
+            rc = OPB_ERR_SUBSET_INDEX;
+        }
+    });
+    return g != OPB_OK ? g : rc;
+}
+
+int opb_hand_peaks(opb_context* ctx, const float* dev_heat, int H, int W, double thre, double* host_peaks) {
+    return guarded([&] {
+        OPB_REQUIRE(dev_heat && host_peaks, "null argument");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool pool;
+        HandBuffers hb;
+        hb.labels = pool.alloc_t<int>((size_t)21 * H * W);
+        hb.sums = pool.alloc_t<double>((size_t)21 * H * W);
+        hb.peaks = pool.alloc_t<double>(63, true);
+        hand_peaks_launch2(dev_heat, 1, 21, H, W, thre, hb, nullptr, ctx->stream);
+        ctx->launches += 4;
+        OPB_CUDA(cudaMemcpyAsync(host_peaks, hb.peaks, 63 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+int opb_conv2d(opb_context* ctx, const void* dev_in, int n, int h, int w, int cin, const float* weight, const float* bias,
+               int cout, int k, int relu, int pool, int out_fp32, void* dev_out, int impl) {
+    return guarded([&] {
+        OPB_REQUIRE(cin % 64 == 0, "opb_conv2d: cin must be a multiple of 64");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool dp;
+        const int bn = cout <= 64 ? 64 : 128;
+        const int cout_pad = (cout + bn - 1) / bn * bn;
+        const int cout_store = (cout + 7) / 8 * 8;
+        const int taps = k * k;
+        const size_t K = (size_t)taps * cin;
+        std::vector<__nv_bfloat16> wd((size_t)cout_pad * K, __float2bfloat16_rn(0.f));
+        for (int co = 0; co < cout; ++co)
+            for (int t = 0; t < taps; ++t)
+                for (int c = 0; c < cin; ++c)
+                    wd[(size_t)co * K + (size_t)t * cin + c] = __float2bfloat16_rn(weight[((size_t)co * cin + c) * taps + t]);
+        std::vector<float> bd(cout_pad, 0.f);
+        for (int co = 0; co < cout; ++co) bd[co] = bias[co];
+        ConvOp op;
+        op.in.base = (void*)dev_in; op.in.n = n; op.in.h = h; op.in.w = w; op.in.c = cin; op.in.cstride = cin; op.in.elem = 2;
+        op.out.base = dev_out; op.out.n = n; op.out.h = pool ? h / 2 : h; op.out.w = pool ? w / 2 : w;
+        op.out.c = cout_store; op.out.cstride = cout_store; op.out.elem = out_fp32 ? 4 : 2;
+        op.w = dp.upload(wd);
+        op.bias = dp.upload(bd);
+        op.cout_pad = cout_pad; op.cout_store = cout_store; op.ks = k; op.relu = relu != 0; op.pool = pool != 0;
+        if (impl == 0)
+            conv_tc_launch({op}, bn, ctx->stream, ctx->num_sms);
+        else
+            conv_direct_launch(op, ctx->stream);
+        ctx->launches += 1;
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,205 @@
+// Hand key-point extraction on the device -- src/hand.py:59-75 and util.npmax (src/util.py:205-210).
+//
+// Per key-point map (21 of the 22 channels) the reference: smooths with gaussian_filter(sigma=3) in float64,
+// thresholds at 0.03, labels the binary mask with 8-connectivity, keeps the component with the largest sum of RAW
+// map values (first maximum on ties; skimage numbers components in raster order of their first pixel), zeroes
+// everything else and takes the first row-major argmax.
+//
+//   hand_smooth_kernel   same exact-float64 separable filter as peaks.cu; writes label[i] = i for mask pixels,
+//                        -1 elsewhere
+//   hand_merge_kernel    union-find over the W / NW / N / NE neighbours (atomicMin hooking); roots are the
+//                        smallest linear index of a component == raster order of first pixels
+//   hand_flatten_kernel  path compression + per-root float64 sums of raw values (atomicAdd)
+//   hand_select_kernel   one CTA per map: argmax over roots (sum desc, root asc), then argmax over pixels of
+//                        (label == best ? raw : 0) (value desc, index asc)
+// The component sums are accumulated in a different order than numpy's pairwise np.sum, so the choice of
+// component is identical unless two sums agree to ~1e-12 relative (tests check the margin).
+#include "opb_common.cuh"
+
+namespace opb {
+namespace {
+
+constexpr int TW = 32, TH = 16, R = kGaussRadius;
+constexpr int RAW_W = TW + 2 * R, RAW_H = TH + 2 * R;
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i >= n ? period - 1 - i : i;
+}
+
+__global__ void __launch_bounds__(256) hand_smooth_kernel(const float* __restrict__ heat, int h, int w, int chan_stride_maps,
+                                                          const GaussTaps taps, double thre, int* __restrict__ labels,
+                                                          double* __restrict__ smoothed_out) {
+    __shared__ double raw[RAW_H][RAW_W];
+    __shared__ double ver[TH][RAW_W];
+    const int m = blockIdx.z;                                   // map index = crop * 21 + part
+    const int crop = m / 21, part = m - crop * 21;
+    const float* map = heat + ((size_t)crop * chan_stride_maps + part) * h * w;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < RAW_H * RAW_W; i += blockDim.x) {
+        const int ry = i / RAW_W, rx = i - ry * RAW_W;
+        raw[ry][rx] = (double)map[(size_t)reflect_idx(y0 - R + ry, h) * w + reflect_idx(x0 - R + rx, w)];
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * RAW_W; i += blockDim.x) {
+        const int r = i / RAW_W, c = i - r * RAW_W;
+        double acc = __dmul_rn(raw[r + R][c], taps.w[0]);
+#pragma unroll
+        for (int d = R; d >= 1; --d)
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(raw[r + R - d][c], raw[r + R + d][c]), taps.w[d]));
+        ver[r][c] = acc;
+    }
+    __syncthreads();
+    for (int i = tid; i < TH * TW; i += blockDim.x) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int y = y0 + ty, x = x0 + tx;
+        if (y >= h || x >= w) continue;
+        double acc = __dmul_rn(ver[ty][tx + R], taps.w[0]);
+#pragma unroll
+        for (int d = R; d >= 1; --d)
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ver[ty][tx + R - d], ver[ty][tx + R + d]), taps.w[d]));
+        const size_t idx = (size_t)m * h * w + (size_t)y * w + x;
+        labels[idx] = acc > thre ? y * w + x : -1;
+        if (smoothed_out) smoothed_out[idx] = acc;
+    }
+}
+
+// parent reads go to L2 (__ldcg): other CTAs hook roots with atomics while we walk
+__device__ __forceinline__ int uf_find(const int* L, int x) {
+    int p = __ldcg(L + x);
+    while (p != x) {
+        x = p;
+        p = __ldcg(L + x);
+    }
+    return x;
+}
+__device__ void uf_union(int* L, int a, int b) {
+    while (true) {
+        a = uf_find(L, a);
+        b = uf_find(L, b);
+        if (a == b) return;
+        if (a > b) {
+            const int t = a;
+            a = b;
+            b = t;
+        }
+        const int old = atomicMin(&L[b], a);        // hook the larger root under the smaller
+        if (old == b) return;
+        b = old;
+    }
+}
+
+__global__ void hand_merge_kernel(int* __restrict__ labels, int h, int w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w) return;
+    int* L = labels + (size_t)blockIdx.z * h * w;
+    const int i = y * w + x;
+    if (L[i] < 0) return;
+    if (x > 0 && L[i - 1] >= 0) uf_union(L, i, i - 1);
+    if (y > 0) {
+        if (L[i - w] >= 0) uf_union(L, i, i - w);
+        if (x > 0 && L[i - w - 1] >= 0) uf_union(L, i, i - w - 1);
+        if (x + 1 < w && L[i - w + 1] >= 0) uf_union(L, i, i - w + 1);
+    }
+}
+
+__global__ void hand_flatten_kernel(const float* __restrict__ heat, int chan_stride_maps, int* __restrict__ labels,
+                                    double* __restrict__ sums, int h, int w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w) return;
+    const int m = blockIdx.z;
+    const int crop = m / 21, part = m - crop * 21;
+    int* L = labels + (size_t)m * h * w;
+    const int i = y * w + x;
+    if (L[i] < 0) return;
+    const int root = uf_find(L, i);
+    // every thread only ever lowers its own entry to its root: concurrent finds stay valid
+    if (root != i) L[i] = root;
+    const float v = heat[((size_t)crop * chan_stride_maps + part) * h * w + i];
+    atomicAdd(&sums[(size_t)m * h * w + root], (double)v);
+}
+
+struct Best {
+    double v;
+    int idx;
+};
+__device__ __forceinline__ Best better(Best a, Best b) {       // value descending, index ascending
+    if (b.idx >= 0 && (a.idx < 0 || b.v > a.v || (b.v == a.v && b.idx < a.idx))) return b;
+    return a;
+}
+__device__ Best block_best(Best mine, Best* s) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        Best other;
+        other.v = __shfl_xor_sync(0xffffffffu, mine.v, o);
+        other.idx = __shfl_xor_sync(0xffffffffu, mine.idx, o);
+        mine = better(mine, other);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) s[warp] = mine;
+    __syncthreads();
+    Best r = s[0];
+    for (int i = 1; i < (int)(blockDim.x >> 5); ++i) r = better(r, s[i]);
+    return r;
+}
+
+__global__ void __launch_bounds__(1024) hand_select_kernel(const float* __restrict__ heat, int chan_stride_maps,
+                                                           const int* __restrict__ labels,
+                                                           const double* __restrict__ sums, int h, int w,
+                                                           double* __restrict__ peaks) {
+    __shared__ Best s[32];
+    const int m = blockIdx.x;
+    const int crop = m / 21, part = m - crop * 21;
+    const int n = h * w;
+    const int* L = labels + (size_t)m * n;
+    const double* S = sums + (size_t)m * n;
+    const float* map = heat + ((size_t)crop * chan_stride_maps + part) * n;
+    Best mine{0.0, -1};
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (L[i] == i) mine = better(mine, Best{S[i], i});      // roots only
+    const Best comp = block_best(mine, s);
+    if (comp.idx < 0) {                                          // nothing above the threshold: [0, 0, 0]
+        if (threadIdx.x < 3) peaks[(size_t)m * 3 + threadIdx.x] = 0.0;
+        return;
+    }
+    mine = Best{0.0, -1};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const double v = L[i] == comp.idx ? (double)map[i] : 0.0;   // map_ori[label_img == 0] = 0
+        mine = better(mine, Best{v, i});
+    }
+    const Best px = block_best(mine, s);
+    if (threadIdx.x == 0) {
+        peaks[(size_t)m * 3 + 0] = (double)(px.idx % w);
+        peaks[(size_t)m * 3 + 1] = (double)(px.idx / w);
+        peaks[(size_t)m * 3 + 2] = px.v;
+    }
+}
+
+}  // namespace
+
+// heat: planar (n_crops * chan_stride_maps, h, w) fp32, the first 21 planes of each crop are used
+void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_maps, int h, int w, double thre,
+                        HandBuffers hb, double* smoothed_out, cudaStream_t stream) {
+    const int maps = n_crops * 21;
+    OPB_REQUIRE(maps <= 65535, "hand_peaks: too many crops in one batch");
+    OPB_CUDA(cudaMemsetAsync(hb.sums, 0, sizeof(double) * (size_t)maps * h * w, stream));
+    dim3 g1(cdiv(w, TW), cdiv(h, TH), maps);
+    hand_smooth_kernel<<<g1, 256, 0, stream>>>(heat_planar, h, w, chan_stride_maps, gauss_taps_sigma3(), thre,
+                                               hb.labels, smoothed_out);
+    OPB_CUDA(cudaGetLastError());
+    dim3 g2(cdiv(w, 128), h, maps);
+    hand_merge_kernel<<<g2, 128, 0, stream>>>(hb.labels, h, w);
+    OPB_CUDA(cudaGetLastError());
+    hand_flatten_kernel<<<g2, 128, 0, stream>>>(heat_planar, chan_stride_maps, hb.labels, hb.sums, h, w);
+    OPB_CUDA(cudaGetLastError());
+    hand_select_kernel<<<maps, 1024, 0, stream>>>(heat_planar, chan_stride_maps, hb.labels, hb.sums, h, w, hb.peaks);
+    OPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace opb

@@ -1,0 +1,106 @@
+// Host-side runtime of the library: contexts, network weights, execution plans, sessions.
+#pragma once
+#include "opb_common.cuh"
+#include <functional>
+#include <memory>
+
+namespace opb {
+
+struct LayerSpec {
+    std::string name;
+    int cin, cout, k;
+    bool relu;
+    bool pool_after;      // a 2x2/2 max-pool follows this layer (src/model.py:37,40,45)
+};
+const std::vector<LayerSpec>& layer_specs(int kind);
+
+// device weights of one layer in the layout the kernels consume
+struct DevLayer {
+    __nv_bfloat16* w = nullptr;   // [cout_pad][k*k*cin_dev] bf16 (tensor-core layers)
+    float* w_first = nullptr;     // [27][64] fp32 holding bf16-rounded values (conv1_1 only)
+    float* bias = nullptr;        // [cout_pad] fp32
+    int cin_dev = 0;              // channels of the device input view (padded / permuted)
+    int cout_pad = 0, cout_store = 0, block_n = 128, k = 3;
+    bool relu = true;
+};
+
+struct HostLayer {
+    std::vector<float> w, b;
+    int cout = 0, cin = 0, k = 0;
+};
+
+}  // namespace opb
+
+struct opb_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int num_sms = 148;
+    int64_t launches = 0;
+    // scratch for the stage-level entry points
+    std::vector<void*> owned;
+    ~opb_context();
+};
+
+struct opb_net {
+    opb_context* ctx = nullptr;
+    int kind = OPB_NET_BODY;
+    std::map<std::string, opb::HostLayer> host;
+    std::map<std::string, opb::DevLayer> dev;
+    bool finalized = false;
+    std::vector<void*> owned;
+    ~opb_net();
+};
+
+namespace opb {
+
+// a device allocation list freed with its owner
+struct DevPool {
+    std::vector<void*> ptrs;
+    size_t bytes = 0;
+    void* alloc(size_t n, bool zero = false);
+    template <typename T>
+    T* alloc_t(size_t count, bool zero = false) { return (T*)alloc(count * sizeof(T), zero); }
+    template <typename T>
+    T* upload(const std::vector<T>& v) {
+        T* d = alloc_t<T>(v.size() ? v.size() : 1);
+        if (!v.empty()) OPB_CUDA(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return d;
+    }
+    void release();
+    ~DevPool() { release(); }
+};
+
+// CNN execution plan for a fixed set of input shapes (one entry per scale)
+struct NetShape {
+    int n, hp, wp;
+    bool operator<(const NetShape& o) const {
+        return n != o.n ? n < o.n : (hp != o.hp ? hp < o.hp : wp < o.wp);
+    }
+};
+struct NetPlan {
+    DevPool pool;
+    std::vector<NetShape> shapes;
+    std::vector<uint8_t*> in_u8;                // per scale: (n, hp, wp, 3) uint8 input
+    std::vector<float*> out_paf, out_heat;      // per scale: fp32 NHWC (cstride 40 / 24); hand: heat only
+    std::vector<std::function<void(cudaStream_t)>> steps;
+    std::vector<ConvLaunch*> launches;
+    int kernel_launches = 0;
+    double gflop = 0;                           // algorithmic FLOPs (un-padded channels), for the roofline
+    void run(cudaStream_t s) const {
+        for (auto& f : steps) f(s);
+    }
+    ~NetPlan();
+};
+std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape>& shapes);
+void finalize_net(opb_net* net);
+
+// cubic tap tables (host)
+struct CubicTaps {
+    std::vector<int> first;       // first source index (unclamped), per destination index
+    std::vector<float> coef;      // [dst][4] float32 coefficients
+};
+CubicTaps cubic_taps(int src, int dst, double scale);
+int resize_dsize(int n, double f);                 // cv2: saturate_cast<int>(n*f), round half to even
+void composite_taps(int n_net, int n_resized, int n_orig, std::vector<int>& first, std::vector<float>& w6);
+
+}  // namespace opb

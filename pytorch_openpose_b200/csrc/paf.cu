@@ -1,0 +1,289 @@
+// PAF line-integral scoring, greedy per-limb matching and person (subset) assembly -- src/body.py:96-212,
+// entirely on the device, in float64 with the reference's operation order so that every threshold decision,
+// sort position and accumulated score is bit-identical to the float64 Python code run on the same maps.
+// Compiled with --fmad=false; multiplies and adds that numpy performs as separate roundings use _rn intrinsics.
+//
+//   paf_score_kernel  one warp per candidate pair (i in part A, j in part B) of a limb: lanes 0..9 gather the
+//                     mid_num=10 nearest-pixel samples of the limb's two PAF channels (np.linspace + round
+//                     half-even), lane 0 folds them in index order (Python's builtin sum), applies the distance
+//                     prior min(0.5*H/norm-1, 0) and both criteria, and appends survivors to the limb's list.
+//   limb_match_kernel one CTA per limb: rank-sorts survivors by (score desc, i asc, j asc) == Python's stable
+//                     sorted(..., reverse=True) over the (i, j) loop order, then walks them greedily.
+//   assemble_kernel   one warp: the reference's sequential row merge (found==1 / found==2 / new row, k < 17),
+//                     rows kept in shared memory, row search parallel over lanes, then pruning.
+#include "opb_common.cuh"
+
+namespace opb {
+namespace {
+
+constexpr int kLimbs = 19;
+constexpr int kMid = 10;
+__constant__ int c_limb_a[kLimbs] = {1, 1, 2, 3, 5, 6, 1, 8, 9, 1, 11, 12, 1, 0, 14, 0, 15, 2, 5};     // limbSeq-1
+__constant__ int c_limb_b[kLimbs] = {2, 5, 3, 4, 6, 7, 8, 9, 10, 11, 12, 13, 0, 14, 16, 15, 17, 16, 17};
+__constant__ int c_paf_x[kLimbs] = {12, 20, 14, 16, 22, 24, 0, 2, 4, 6, 8, 10, 28, 30, 34, 32, 36, 18, 26};  // mapIdx-19
+
+constexpr int ST_PAIR_OVERFLOW = 1, ST_CONN_OVERFLOW = 2, ST_SUBSET_OVERFLOW = 4, ST_INDEX_ERROR = 8;
+
+__global__ void __launch_bounds__(256) paf_score_kernel(const float* __restrict__ paf, int H, int W,
+                                                        const double* __restrict__ cand,
+                                                        const int* __restrict__ part_begin, LimbBuffers lb,
+                                                        double thre2) {
+    const int k = blockIdx.y;
+    const int pa = c_limb_a[k], pb = c_limb_b[k];
+    const int a0 = part_begin[pa], nA = part_begin[pa + 1] - a0;
+    const int b0 = part_begin[pb], nB = part_begin[pb + 1] - b0;
+    const long long pairs = (long long)nA * nB;
+    const int lane = threadIdx.x & 31;
+    const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const float* px_map = paf + (size_t)c_paf_x[k] * H * W;
+    const float* py_map = px_map + (size_t)H * W;
+
+    for (long long pr = warp0; pr < pairs; pr += nwarps) {
+        const int i = (int)(pr / nB), j = (int)(pr - (long long)i * nB);
+        const double ax = cand[(size_t)(a0 + i) * 4], ay = cand[(size_t)(a0 + i) * 4 + 1];
+        const double bx = cand[(size_t)(b0 + j) * 4], by = cand[(size_t)(b0 + j) * 4 + 1];
+        const double vx = bx - ax, vy = by - ay;                               // exact (integers)
+        const double norm = __dadd_rn(sqrt(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy))), 1e-10);
+        const double ux = vx / norm, uy = vy / norm;
+        double dot = 0.0;
+        if (lane < kMid) {
+            // np.linspace(a, b, 10): arange(10) * ((b-a)/9) + a, last sample forced to b
+            double sx, sy;
+            if (lane == kMid - 1) {
+                sx = bx;
+                sy = by;
+            } else {
+                sx = __dadd_rn(__dmul_rn((double)lane, vx / 9.0), ax);
+                sy = __dadd_rn(__dmul_rn((double)lane, vy / 9.0), ay);
+            }
+            const int xi = (int)rint(sx), yi = (int)rint(sy);                  // int(round()): half to even
+            const double fx = (double)px_map[(size_t)yi * W + xi];
+            const double fy = (double)py_map[(size_t)yi * W + xi];
+            dot = __dadd_rn(__dmul_rn(fx, ux), __dmul_rn(fy, uy));
+        }
+        const unsigned above = __ballot_sync(0xffffffffu, lane < kMid && dot > thre2);
+        double total = 0.0;                                                    // sum(): 0 + d0 + d1 + ...
+#pragma unroll
+        for (int s = 0; s < kMid; ++s) total = __dadd_rn(total, __shfl_sync(0xffffffffu, dot, s));
+        if (lane == 0) {
+            double prior = __dadd_rn(__dmul_rn(0.5, (double)H) / norm, -1.0);
+            if (!(prior < 0.0)) prior = 0.0;                                   // min(x, 0)
+            const double score = __dadd_rn(total / (double)kMid, prior);
+            if (__popc(above) > 8 && score > 0.0) {                            // > 0.8 * 10
+                const int slot = atomicAdd(&lb.cand_count[k], 1);
+                if (slot < lb.pair_capacity) {
+                    lb.cand_score[(size_t)k * lb.pair_capacity + slot] = score;
+                    lb.cand_ij[((size_t)k * lb.pair_capacity + slot) * 2] = i;
+                    lb.cand_ij[((size_t)k * lb.pair_capacity + slot) * 2 + 1] = j;
+                } else {
+                    atomicOr(lb.status, ST_PAIR_OVERFLOW);
+                }
+            }
+        }
+    }
+}
+
+// order: score descending, then original (i, j) loop order
+__device__ __forceinline__ bool cand_before(double s1, long long o1, double s2, long long o2) {
+    return s1 > s2 || (s1 == s2 && o1 < o2);
+}
+
+__global__ void __launch_bounds__(256) limb_match_kernel(const int* __restrict__ part_begin, LimbBuffers lb,
+                                                         int* __restrict__ order /*[19][pair_capacity]*/,
+                                                         unsigned char* __restrict__ used /*[19][2][max_part]*/,
+                                                         int max_part) {
+    __shared__ double s_score[256];
+    __shared__ long long s_ord[256];
+    const int k = blockIdx.x;
+    const int pa = c_limb_a[k], pb = c_limb_b[k];
+    const int a0 = part_begin[pa], nA = part_begin[pa + 1] - a0;
+    const int b0 = part_begin[pb], nB = part_begin[pb + 1] - b0;
+    const int n = min(lb.cand_count[k], lb.pair_capacity);
+    const double* sc = lb.cand_score + (size_t)k * lb.pair_capacity;
+    const int* ij = lb.cand_ij + (size_t)k * lb.pair_capacity * 2;
+    int* ord = order + (size_t)k * lb.pair_capacity;
+    unsigned char* usedA = used + (size_t)k * 2 * max_part;
+    unsigned char* usedB = usedA + max_part;
+
+    if (threadIdx.x == 0) lb.conn_count[k] = (nA == 0 || nB == 0) ? -1 : 0;   // -1: limb in special_k
+    if (nA == 0 || nB == 0 || n == 0) return;
+
+    for (int t = threadIdx.x; t < nA; t += blockDim.x) usedA[t] = 0;
+    for (int t = threadIdx.x; t < nB; t += blockDim.x) usedB[t] = 0;
+
+    // rank sort (candidates are unique in (i, j), so ranks are a permutation)
+    for (int base_i = 0; base_i < n; base_i += blockDim.x) {
+        const int c = base_i + threadIdx.x;
+        const double my_s = c < n ? sc[c] : 0.0;
+        const long long my_o = c < n ? (long long)ij[2 * c] * nB + ij[2 * c + 1] : 0;
+        int rank = 0;
+        for (int base = 0; base < n; base += 256) {
+            const int t = base + threadIdx.x;
+            if (t < n) {
+                s_score[threadIdx.x] = sc[t];
+                s_ord[threadIdx.x] = (long long)ij[2 * t] * nB + ij[2 * t + 1];
+            }
+            __syncthreads();
+            const int m = min(256, n - base);
+            if (c < n)
+                for (int q = 0; q < m; ++q) rank += cand_before(s_score[q], s_ord[q], my_s, my_o);
+            __syncthreads();
+        }
+        if (c < n) ord[rank] = c;
+    }
+    __syncthreads();
+
+    // greedy walk (src/body.py:143-150) -- inherently sequential; one thread, inputs are L1/L2 resident
+    if (threadIdx.x == 0) {
+        const int limit = min(nA, nB);
+        int count = 0;
+        double* conn = lb.conn + (size_t)k * lb.conn_capacity * 5;
+        for (int r = 0; r < n && count < limit; ++r) {
+            const int c = ord[r];
+            const int i = ij[2 * c], j = ij[2 * c + 1];
+            if (usedA[i] || usedB[j]) continue;
+            usedA[i] = 1;
+            usedB[j] = 1;
+            if (count < lb.conn_capacity) {
+                double* row = conn + (size_t)count * 5;
+                row[0] = (double)(a0 + i);      // candidate id of A (ids are global sorted positions)
+                row[1] = (double)(b0 + j);
+                row[2] = sc[c];
+                row[3] = (double)i;
+                row[4] = (double)j;
+            } else {
+                atomicOr(lb.status, ST_CONN_OVERFLOW);
+            }
+            ++count;
+        }
+        lb.conn_count[k] = min(count, lb.conn_capacity);
+    }
+}
+
+// ---- subset assembly: one warp, rows in dynamic shared memory -----------------------------------------
+__global__ void __launch_bounds__(32) assemble_kernel(const double* __restrict__ cand, LimbBuffers lb) {
+    extern __shared__ double rows[];                 // [subset_capacity][20]
+    const int lane = threadIdx.x;
+    int nrows = 0;
+    bool fail = false;
+
+    for (int k = 0; k < kLimbs && !fail; ++k) {
+        const int ncon = lb.conn_count[k];
+        if (ncon < 0) continue;                      // special_k
+        const int ia = c_limb_a[k], ib = c_limb_b[k];
+        const double* conn = lb.conn + (size_t)k * lb.conn_capacity * 5;
+        for (int c = 0; c < ncon && !fail; ++c) {
+            const double idA = conn[c * 5], idB = conn[c * 5 + 1], limb_score = conn[c * 5 + 2];
+            // rows j with subset[j][indexA] == partAs[i] or subset[j][indexB] == partBs[i]
+            int found = 0, j1 = -1, j2 = -1;
+            for (int base = 0; base < nrows; base += 32) {
+                const int j = base + lane;
+                const bool m = j < nrows && (rows[j * 20 + ia] == idA || rows[j * 20 + ib] == idB);
+                unsigned mask = __ballot_sync(0xffffffffu, m);
+                while (mask) {
+                    const int b = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    if (found == 0) j1 = base + b;
+                    else if (found == 1) j2 = base + b;
+                    ++found;
+                }
+            }
+            if (found > 2) {                         // reference: IndexError at src/body.py:173
+                fail = true;
+                if (lane == 0) atomicOr(lb.status, ST_INDEX_ERROR);
+                break;
+            }
+            if (found == 2) {
+                // disjoint?  (membership == 2 nowhere over the 18 part slots)
+                const bool both = lane < 18 && rows[j1 * 20 + lane] >= 0.0 && rows[j2 * 20 + lane] >= 0.0;
+                const bool overlap = __ballot_sync(0xffffffffu, both) != 0;
+                if (!overlap) {
+                    if (lane < 18) rows[j1 * 20 + lane] = rows[j1 * 20 + lane] + (rows[j2 * 20 + lane] + 1.0);
+                    if (lane == 18) rows[j1 * 20 + 18] = (rows[j1 * 20 + 18] + rows[j2 * 20 + 18]) + limb_score;
+                    if (lane == 19) rows[j1 * 20 + 19] = rows[j1 * 20 + 19] + rows[j2 * 20 + 19];
+                    __syncwarp();
+                    // np.delete(subset, j2, 0): shift the tail up by one row
+                    const int first = j2 * 20, last = (nrows - 1) * 20;
+                    for (int t = first; t < last; t += 32) {
+                        const int e = t + lane;
+                        double v = 0.0;
+                        if (e < last) v = rows[e + 20];
+                        __syncwarp();
+                        if (e < last) rows[e] = v;
+                        __syncwarp();
+                    }
+                    --nrows;
+                } else if (lane == 0) {
+                    rows[j1 * 20 + ib] = idB;
+                    rows[j1 * 20 + 19] += 1.0;
+                    rows[j1 * 20 + 18] += cand[(size_t)(int)idB * 4 + 2] + limb_score;
+                }
+            } else if (found == 1) {
+                if (lane == 0 && rows[j1 * 20 + ib] != idB) {
+                    rows[j1 * 20 + ib] = idB;
+                    rows[j1 * 20 + 19] += 1.0;
+                    rows[j1 * 20 + 18] += cand[(size_t)(int)idB * 4 + 2] + limb_score;
+                }
+            } else if (k < 17) {
+                if (nrows >= lb.subset_capacity) {
+                    fail = true;
+                    if (lane == 0) atomicOr(lb.status, ST_SUBSET_OVERFLOW);
+                    break;
+                }
+                if (lane < 18) rows[nrows * 20 + lane] = lane == ia ? idA : (lane == ib ? idB : -1.0);
+                if (lane == 18)
+                    rows[nrows * 20 + 18] = ((0.0 + cand[(size_t)(int)idA * 4 + 2]) + cand[(size_t)(int)idB * 4 + 2]) + limb_score;
+                if (lane == 19) rows[nrows * 20 + 19] = 2.0;
+                ++nrows;
+            }
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+    // prune (src/body.py:204-208) and write out in order
+    int out = 0;
+    for (int base = 0; base < nrows; base += 32) {
+        const int j = base + lane;
+        bool keep = false;
+        if (j < nrows) {
+            const double parts = rows[j * 20 + 19], score = rows[j * 20 + 18];
+            keep = !(parts < 4.0 || score / parts < 0.4);
+        }
+        const unsigned mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            const int dst = out + __popc(mask & ((1u << lane) - 1));
+            for (int q = 0; q < 20; ++q) lb.subset[(size_t)dst * 20 + q] = rows[j * 20 + q];
+        }
+        out += __popc(mask);
+    }
+    if (lane == 0) {
+        *lb.subset_count = out;
+        lb.status[1] = nrows;
+    }
+}
+
+}  // namespace
+
+// scratch_order: int[19*pair_capacity]; scratch_used: uchar[19*2*max_part]
+void paf_group_launch2(const float* paf_planar, int H, int W, const double* candidates, const int* part_begin,
+                       LimbBuffers lb, double thre2, int* scratch_order, unsigned char* scratch_used, int max_part,
+                       cudaStream_t stream) {
+    OPB_REQUIRE(lb.subset_capacity * 20 * 8 <= 200 * 1024, "subset capacity limited by shared memory (<= 1280 rows)");
+    OPB_CUDA(cudaMemsetAsync(lb.cand_count, 0, sizeof(int) * kLimbs, stream));
+    OPB_CUDA(cudaMemsetAsync(lb.status, 0, sizeof(int) * 4, stream));
+    dim3 grid(64, kLimbs);
+    paf_score_kernel<<<grid, 256, 0, stream>>>(paf_planar, H, W, candidates, part_begin, lb, thre2);
+    OPB_CUDA(cudaGetLastError());
+    limb_match_kernel<<<kLimbs, 256, 0, stream>>>(part_begin, lb, scratch_order, scratch_used, max_part);
+    OPB_CUDA(cudaGetLastError());
+    static bool attr = false;
+    if (!attr) {
+        OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    assemble_kernel<<<1, 32, (size_t)lb.subset_capacity * 20 * 8, stream>>>(candidates, lb);
+    OPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace opb

@@ -1,0 +1,171 @@
+// Gaussian smoothing + 4-neighbour NMS + ordered peak list (src/body.py:70-94).
+//
+// The reference smooths each of the 18 part maps with scipy.ndimage.gaussian_filter(sigma=3) in float64
+// (25 taps, 'reflect' border, axis 0 then axis 1) and keeps pixels that are >= their four neighbours (zero
+// outside the image) and > thre1.  Ties and plateaus make the >= comparisons sensitive to the last bit, so the
+// device filter reproduces scipy's arithmetic exactly: float64, centre tap first, then the symmetric pairs
+// from the far tap inwards, pair summed before the multiply, no FMA contraction (this file is compiled with
+// --fmad=false and uses explicit _rn intrinsics).  One CTA smooths a 32x16 tile from a shared-memory halo
+// tile; tiles whose raw maximum is <= thre1 are skipped (the weights are positive and sum to one, so the
+// smoothed value cannot exceed the raw maximum of its window).
+//
+// Peaks are appended unordered with warp-aggregated atomics and then rank-sorted by (part, y, x), which is
+// the reference's order (part-major, np.nonzero row-major); the rank is the candidate id.
+#include "opb_common.cuh"
+
+namespace opb {
+namespace {
+
+constexpr int TW = 32, TH = 16, R = kGaussRadius;
+constexpr int RAW_W = TW + 2 + 2 * R;   // 58: tile + 1-pixel NMS ring + filter halo
+constexpr int RAW_H = TH + 2 + 2 * R;   // 42
+constexpr int SM_W = TW + 2;            // 34
+constexpr int SM_H = TH + 2;            // 18
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // scipy 'reflect' (d c b a | a b c d | d c b a), valid for any offset
+    const int period = 2 * n;
+    i %= period;
+    if (i < 0) i += period;
+    return i >= n ? period - 1 - i : i;
+}
+
+__global__ void __launch_bounds__(256) smooth_nms_kernel(const float* __restrict__ heat, int H, int W,
+                                                         const GaussTaps taps, double thre, PeakBuffers pb,
+                                                         double* __restrict__ smoothed_out) {
+    __shared__ double raw[RAW_H][RAW_W];
+    __shared__ double ver[SM_H][RAW_W];
+    __shared__ double sm[SM_H][SM_W];
+    __shared__ int any_above;
+
+    const int part = blockIdx.z;
+    const float* map = heat + (size_t)part * H * W;
+    const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    const int tid = threadIdx.x;
+
+    if (tid == 0) any_above = 0;
+    __syncthreads();
+    // The taps are positive and sum to one, so a smoothed value cannot exceed the raw maximum of its window
+    // (up to ~1e-15 relative rounding): a tile whose whole halo window stays 1e-6 below thre has no peak.
+    const double skip_below = thre > 0 ? thre * 0.999999 : thre * 1.000001;
+    bool above = false;
+    for (int i = tid; i < RAW_H * RAW_W; i += blockDim.x) {
+        const int ry = i / RAW_W, rx = i - ry * RAW_W;
+        const float v = map[(size_t)reflect_idx(y0 - 1 - R + ry, H) * W + reflect_idx(x0 - 1 - R + rx, W)];
+        raw[ry][rx] = (double)v;
+        above |= !((double)v < skip_below);                    // NaN counts as "above": never skipped
+    }
+    if (above) any_above = 1;
+    __syncthreads();
+    if (!any_above && smoothed_out == nullptr) return;
+
+    // vertical pass (scipy axis 0) for the SM_H rows x RAW_W columns that the horizontal pass needs
+    for (int i = tid; i < SM_H * RAW_W; i += blockDim.x) {
+        const int r = i / RAW_W, c = i - r * RAW_W;
+        double acc = __dmul_rn(raw[r + R][c], taps.w[0]);
+#pragma unroll
+        for (int d = R; d >= 1; --d)
+            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(raw[r + R - d][c], raw[r + R + d][c]), taps.w[d]));
+        ver[r][c] = acc;
+    }
+    __syncthreads();
+    // horizontal pass (scipy axis 1); positions outside the image are the NMS zero border
+    for (int i = tid; i < SM_H * SM_W; i += blockDim.x) {
+        const int r = i / SM_W, c = i - r * SM_W;
+        const int y = y0 - 1 + r, x = x0 - 1 + c;
+        double acc = 0.0;
+        if (y >= 0 && y < H && x >= 0 && x < W) {
+            acc = __dmul_rn(ver[r][c + R], taps.w[0]);
+#pragma unroll
+            for (int d = R; d >= 1; --d)
+                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ver[r][c + R - d], ver[r][c + R + d]), taps.w[d]));
+        }
+        sm[r][c] = acc;
+    }
+    __syncthreads();
+
+    for (int i = tid; i < TH * TW; i += blockDim.x) {
+        const int ty = i / TW, tx = i - ty * TW;
+        const int y = y0 + ty, x = x0 + tx;
+        bool peak = false;
+        if (y < H && x < W) {
+            const double v = sm[ty + 1][tx + 1];
+            if (smoothed_out) smoothed_out[((size_t)part * H + y) * W + x] = v;
+            peak = v >= sm[ty][tx + 1] && v >= sm[ty + 2][tx + 1] && v >= sm[ty + 1][tx] && v >= sm[ty + 1][tx + 2] &&
+                   v > thre;
+        }
+        const unsigned ballot = __ballot_sync(0xffffffffu, peak);
+        if (ballot) {
+            const int lane = tid & 31;
+            int base = 0;
+            if (lane == 0) base = atomicAdd(pb.count, __popc(ballot));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (peak) {
+                const int slot = base + __popc(ballot & ((1u << lane) - 1));
+                if (slot < pb.capacity) {
+                    pb.keys[slot] = ((unsigned long long)part << 40) | ((unsigned long long)y << 20) | (unsigned)x;
+                    pb.scores[slot] = map[(size_t)y * W + x];           // RAW score, src/body.py:89
+                }
+            }
+        }
+    }
+}
+
+// rank sort: position = number of smaller keys (keys are unique); also counts peaks per part
+__global__ void __launch_bounds__(256) sort_peaks_kernel(PeakBuffers pb, int parts, int* __restrict__ part_count) {
+    __shared__ unsigned long long sk[256];
+    const int n = min(*pb.count, pb.capacity);
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const unsigned long long key = i < n ? pb.keys[i] : ~0ull;
+    int rank = 0;
+    for (int base = 0; base < n; base += 256) {
+        const int j = base + threadIdx.x;
+        sk[threadIdx.x] = j < n ? pb.keys[j] : ~0ull;
+        __syncthreads();
+        const int m = min(256, n - base);
+        for (int t = 0; t < m; ++t) rank += sk[t] < key;
+        __syncthreads();
+    }
+    if (i < n) {
+        double* c = pb.candidates + (size_t)rank * 4;
+        c[0] = (double)(unsigned)(key & 0xFFFFF);
+        c[1] = (double)(unsigned)((key >> 20) & 0xFFFFF);
+        c[2] = (double)pb.scores[i];
+        c[3] = (double)rank;                                            // cumulative peak id, src/body.py:90
+        atomicAdd(&part_count[(int)(key >> 40)], 1);
+    }
+}
+
+__global__ void part_prefix_kernel(const int* __restrict__ part_count, int* __restrict__ part_begin, int parts) {
+    if (threadIdx.x == 0) {
+        int acc = 0;
+        for (int p = 0; p < parts; ++p) {
+            part_begin[p] = acc;
+            acc += part_count[p];
+        }
+        part_begin[parts] = acc;
+    }
+}
+
+}  // namespace
+
+void smooth_nms_launch(const float* heat_planar, int H, int W, int parts, double thre, PeakBuffers pb,
+                       double* smoothed_out, cudaStream_t stream) {
+    OPB_REQUIRE(H < (1 << 20) && W < (1 << 20), "smooth_nms: image too large for the key packing");
+    OPB_CUDA(cudaMemsetAsync(pb.count, 0, sizeof(int), stream));
+    dim3 grid(cdiv(W, TW), cdiv(H, TH), parts);
+    smooth_nms_kernel<<<grid, 256, 0, stream>>>(heat_planar, H, W, gauss_taps_sigma3(), thre, pb, smoothed_out);
+    OPB_CUDA(cudaGetLastError());
+}
+
+// part_count_scratch: device int[parts]
+void sort_peaks_launch2(PeakBuffers pb, int parts, int* part_count_scratch, cudaStream_t stream) {
+    OPB_CUDA(cudaMemsetAsync(part_count_scratch, 0, sizeof(int) * parts, stream));
+    sort_peaks_kernel<<<cdiv(pb.capacity, 256), 256, 0, stream>>>(pb, parts, part_count_scratch);
+    OPB_CUDA(cudaGetLastError());
+    part_prefix_kernel<<<1, 32, 0, stream>>>(part_count_scratch, pb.part_begin, parts);
+    OPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace opb

@@ -1,0 +1,190 @@
+// Streaming kernels either side of the CNN.
+//
+//   preprocess   : src/body.py:38-39 + src/util.py:12-32 -- cv2.resize(INTER_CUBIC) of the uint8 BGR frame by
+//                  `multiplier`, then pad right/bottom with 128 to a multiple of 8.  The arithmetic follows
+//                  OpenCV's open-source resize exactly (11-bit fixed-point taps, int32 horizontal pass, float
+//                  vertical pass accumulated S3,S2,S1,S0 with separate multiply and add, integer pass for the
+//                  last (3*w) % 8 elements of every row), so it is bit-identical to cv2 with IPP disabled
+//                  (see oracle/openpose_oracle.py::resize_cubic_u8).  The /256-0.5 normalisation and the
+//                  HWC->NCHW transpose of src/body.py:40 are folded into the first convolution.
+//   upsample_avg : src/body.py:54-68 / src/hand.py:52-57 -- x8 cubic upsample, crop of the padding, cubic
+//                  resize to the frame size and the cross-scale average.  Both cubic passes are linear and
+//                  separable, so each axis collapses into one banded operator with <= 6 taps per output
+//                  index (tables built on the host in float64, oracle: composite_upsample_matrix).
+//                  Pass 1 applies the x operator per scale into an L2-resident (C, ho, W) scratch, pass 2
+//                  applies the y operators of all scales, averages and writes the planar (C, H, W) map once.
+#include "opb_common.cuh"
+
+namespace opb {
+namespace {
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+// one thread per output element (y, x, c) of the padded image
+__global__ void preprocess_kernel(const uint8_t* __restrict__ img, int H, int W, uint8_t* __restrict__ out, int h,
+                                  int w, int hp, int wp, const int* __restrict__ xf, const short* __restrict__ xc,
+                                  const int* __restrict__ yf, const short* __restrict__ yc, size_t img_stride,
+                                  size_t out_stride) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;      // element within the padded row (x*3 + c)
+    const int y = blockIdx.y;
+    if (e >= wp * 3) return;
+    img += blockIdx.z * img_stride;
+    out += blockIdx.z * out_stride;
+    uint8_t* o = out + (size_t)y * wp * 3 + e;
+    const int x = e / 3, c = e - x * 3;
+    if (y >= h || x >= w) {
+        *o = 128;                                               // padValue, src/body.py:29
+        return;
+    }
+    const int x0 = xf[x], y0 = yf[y];
+    int cx[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) cx[j] = clampi(x0 + j, 0, W - 1) * 3 + c;
+    int hor[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint8_t* row = img + (size_t)clampi(y0 + k, 0, H - 1) * W * 3;
+        int s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += (int)row[cx[j]] * (int)xc[x * 4 + j];
+        hor[k] = s;
+    }
+    int r;
+    const int nvec = ((w * 3) / 8) * 8;                         // OpenCV: 8-lane SIMD body, scalar tail
+    if (e < nvec) {
+        const float sc = 1.0f / (2048.0f * 2048.0f);
+        float acc = __fmul_rn((float)hor[3], __fmul_rn((float)yc[y * 4 + 3], sc));
+#pragma unroll
+        for (int k = 2; k >= 0; --k)
+            acc = __fadd_rn(acc, __fmul_rn((float)hor[k], __fmul_rn((float)yc[y * 4 + k], sc)));
+        r = __float2int_rn(acc);
+    } else {
+        long long s = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s += (long long)hor[k] * (long long)yc[y * 4 + k];
+        r = (int)((s + (1ll << 21)) >> 22);
+    }
+    *o = (uint8_t)clampi(r, 0, 255);
+}
+
+// pass 1: tmp[c][r][x] = sum_k xw[x][k] * src[r][xfirst[x]+k][c]      (one scale)
+__global__ void upsample_x_kernel(const float* __restrict__ src, int ho, int wo, int cstride, int C, int W,
+                                  const int* __restrict__ xfirst, const float* __restrict__ xw,
+                                  float* __restrict__ tmp) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int c = blockIdx.z;                                   // image * C + channel
+    if (x >= W) return;
+    const int img = c / C, ch = c - img * C;
+    const int f = xfirst[x];
+    const float* s = src + (((size_t)img * ho + r) * wo) * cstride + ch;
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < kUpTaps; ++k) {
+        const int col = min(f + k, wo - 1);                     // weights beyond the footprint are zero
+        acc = fmaf(xw[x * kUpTaps + k], s[(size_t)col * cstride], acc);
+    }
+    tmp[((size_t)c * ho + r) * W + x] = acc;
+}
+
+struct UpYParams {
+    const float* tmp[kMaxScales];     // (C, ho, W) per scale
+    const int* yfirst[kMaxScales];
+    const float* yw[kMaxScales];
+    int ho[kMaxScales];
+    int n_scales;
+    float inv_n;
+};
+
+// pass 2: out[c][y][x] = (1/n) * sum_s sum_k yw_s[y][k] * tmp_s[c][yfirst_s[y]+k][x]
+template <int VEC>
+__global__ void upsample_y_kernel(const __grid_constant__ UpYParams p, int C, int H, int W, float* __restrict__ out) {
+    const int xv = blockIdx.x * blockDim.x + threadIdx.x;
+    const int x = xv * VEC;
+    const int y = blockIdx.y;
+    const int c = blockIdx.z;
+    if (x >= W) return;
+    float acc[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) acc[v] = 0.f;
+    for (int s = 0; s < p.n_scales; ++s) {
+        const int f = p.yfirst[s][y];
+        const int ho = p.ho[s];
+        const float* t = p.tmp[s] + (size_t)c * ho * W + x;
+        float part[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) part[v] = 0.f;
+#pragma unroll
+        for (int k = 0; k < kUpTaps; ++k) {
+            const float wgt = p.yw[s][y * kUpTaps + k];
+            const int r = min(f + k, ho - 1);
+            if (VEC == 4) {
+                const float4 q = *(const float4*)(t + (size_t)r * W);
+                part[0] = fmaf(wgt, q.x, part[0]);
+                part[1 % VEC] = fmaf(wgt, q.y, part[1 % VEC]);
+                part[2 % VEC] = fmaf(wgt, q.z, part[2 % VEC]);
+                part[3 % VEC] = fmaf(wgt, q.w, part[3 % VEC]);
+            } else {
+                part[0] = fmaf(wgt, t[(size_t)r * W], part[0]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) acc[v] += part[v] * p.inv_n;     // heatmap/len(multiplier), then +=
+    }
+    float* o = out + ((size_t)c * H + y) * W + x;
+    if (VEC == 4)
+        *(float4*)o = make_float4(acc[0], acc[1 % VEC], acc[2 % VEC], acc[3 % VEC]);
+    else
+        o[0] = acc[0];
+}
+
+}  // namespace
+
+void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t* out, int h, int w, int hp, int wp,
+                               const int* x_first, const short* x_coef, const int* y_first, const short* y_coef,
+                               cudaStream_t stream) {
+    dim3 grid(cdiv(wp * 3, 256), hp, n);
+    preprocess_kernel<<<grid, 256, 0, stream>>>(img, H, W, out, h, w, hp, wp, x_first, x_coef, y_first, y_coef,
+                                                (size_t)H * W * 3, (size_t)hp * wp * 3);
+    OPB_CUDA(cudaGetLastError());
+}
+
+void preprocess_launch(const uint8_t* img, int H, int W, uint8_t* out, int h, int w, int hp, int wp,
+                       const int* x_first, const short* x_coef, const int* y_first, const short* y_coef,
+                       cudaStream_t stream) {
+    preprocess_launch_batched(img, 1, H, W, out, h, w, hp, wp, x_first, x_coef, y_first, y_coef, stream);
+}
+
+// scratch: float buffer with room for sum_s n_img*C*ho_s*W elements
+void upsample_avg_launch2(const UpsampleScale* scales, int n_scales, int n_img, int C, int H, int W, float* scratch,
+                          float* out_planar, cudaStream_t stream) {
+    const int CT = n_img * C;                                   // planar output has n_img*C channel planes
+    OPB_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "upsample_avg: 1..8 scales");
+    UpYParams p;
+    memset(&p, 0, sizeof(p));
+    p.n_scales = n_scales;
+    p.inv_n = 1.0f / (float)n_scales;
+    size_t off = 0;
+    for (int s = 0; s < n_scales; ++s) {
+        const UpsampleScale& u = scales[s];
+        float* tmp = scratch + off;
+        off += (size_t)CT * u.ho * W;
+        dim3 grid(cdiv(W, 128), u.ho, CT);
+        upsample_x_kernel<<<grid, 128, 0, stream>>>(u.src, u.ho, u.wo, u.cstride, C, W, u.x_first, u.x_w, tmp);
+        OPB_CUDA(cudaGetLastError());
+        p.tmp[s] = tmp;
+        p.yfirst[s] = u.y_first;
+        p.yw[s] = u.y_w;
+        p.ho[s] = u.ho;
+    }
+    if (W % 4 == 0) {
+        dim3 grid(cdiv(W / 4, 64), H, CT);
+        upsample_y_kernel<4><<<grid, 64, 0, stream>>>(p, CT, H, W, out_planar);
+    } else {
+        dim3 grid(cdiv(W, 128), H, CT);
+        upsample_y_kernel<1><<<grid, 128, 0, stream>>>(p, CT, H, W, out_planar);
+    }
+    OPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace opb
