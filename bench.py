@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""Benchmark of the OpenPose hot path (BASELINE.json: body-pose frames/s at 720p, 4 scales).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames-per-step F]
+
+A step is one pass of the whole Body path (preprocess at 4 scales -> CNN -> upsample/average -> Gaussian+NMS ->
+PAF scoring / matching / assembly) over a batch of F synthetic 1280x720 frames on every rank; frames are
+independent, so ranks never exchange data (weak scaling, no collective on the data path).  Rank 0 prints ONE
+JSON line.  `value` is measured with the frames already resident in HBM; `e2e` goes through the same public
+`Body` API with pinned HOST frames, the host->device copy of every frame and the device->host read of every
+result inside the timed region.  `--impl reference` times the CPU restatement of the reference (oracle/) on the
+host cores instead (the reference itself, /root/reference, does not exist on the GPU box)."""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+H, W = 720, 1280
+SCALES = (0.5, 1.0, 1.5, 2.0)
+METRIC = "body_pose_frames_per_sec_720p_4scale"
+GFLOP_PER_FRAME = 3634.8          # algorithmic conv FLOPs of the body net at the four padded sizes
+POOL_FRAMES = 64                  # 64 x 2.76 MB = 177 MB of distinct inputs (> 126 MB L2)
+
+
+def rank_info():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def synth_frames(n, seed):
+    """Structured synthetic frames (blurred noise): cheap to make, not constant."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, (n, H // 8, W // 8, 3), dtype=np.uint8)
+    return np.ascontiguousarray(np.repeat(np.repeat(base, 8, 1), 8, 2))
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for nme, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return p["bf16_tflops_sustained"], p["hbm_gbs"], "measured (MEASURED_PEAKS.json, sustained bf16)"
+    except Exception:
+        return 1400.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_reference_frames(n_frames, threads):
+    """The reference's algorithm on the host cores: the oracle's Body.__call__ restatement, torch CPU fp32 convs,
+    cv2 resizes, scipy-exact Gaussian, Python PAF loops vectorised per limb.  Returns seconds per frame list."""
+    import torch
+    from oracle import openpose_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.make_weights("body", 0)
+    frames = synth_frames(max(n_frames, 1), 123)
+    times = []
+    for i in range(n_frames):
+        t0 = time.perf_counter()
+        O.body_call(frames[i % len(frames)], sd, SCALES, use_cv2=True)
+        times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank, _, world = rank_info()
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    warm = min(args.warmup, 1)
+    steps = max(1, min(args.steps, 12))          # one 720p 4-scale frame is ~10 s of CPU work
+    times = cpu_reference_frames(warm + steps, threads)[warm:]
+    sec = float(np.sum(times))
+    fps = steps / sec
+    line = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "Body() 4-scale [0.5,1.0,1.5,2.0] on synthetic 1280x720 frames, random-init bodypose_model",
+                       "frames_per_step": 1, "note": "steps capped at 12 and warmup at 1: one frame is ~10 s on the host"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                             "sample": "%d full frames (oracle restatement of src/body.py; the reference checkout is not on the GPU box)" % steps},
+            "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    from oracle import openpose_oracle as O            # weights generator only (random-init, seed 0)
+    from pytorch_openpose_b200 import Body, _lib
+    rank, local, world = rank_info()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    F, K, Wm = args.frames_per_step, args.steps, args.warmup
+    body = Body(O.make_weights("body", 0), scale_search=SCALES, device=local)
+    sessions = [body.net.session() for _ in range(args.streams)]
+    frames_host = torch.from_numpy(synth_frames(POOL_FRAMES, 1000 + rank)).pin_memory()
+    frames_dev = frames_host.cuda()
+    host_np = frames_host.numpy()
+    torch.cuda.synchronize()
+
+    def step(step_idx, device_resident):
+        inflight = [False] * len(sessions)
+        for f in range(F):
+            si = f % len(sessions)
+            if inflight[si]:
+                body.collect(sessions[si])
+            idx = (step_idx * F + f) % POOL_FRAMES
+            if device_resident:
+                body.submit((frames_dev[idx].data_ptr(), (H, W)), sessions[si], where=1)
+            else:
+                body.submit(host_np[idx], sessions[si], where=2)
+            inflight[si] = True
+        out = None
+        for si, fl in enumerate(inflight):
+            if fl:
+                out = body.collect(sessions[si])
+        return out
+
+    def timed(device_resident):
+        for w in range(Wm):
+            step(w, device_resident)
+        barrier()
+        l0 = _lib.launch_count(local)
+        sessions[0].mark(0)
+        for k in range(K):
+            step(Wm + k, device_resident)
+        for s in sessions:
+            s.mark(1)
+        torch.cuda.synchronize()
+        ms = max(sessions[0].elapsed_ms(0, s, 1) for s in sessions)
+        launches = _lib.launch_count(local) - l0
+        barrier()
+        return max_over_ranks(ms), launches
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches = timed(True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _ = timed(False)
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), serialised profiled frames ----
+    roof = None
+    stages = {}
+    if rank == 0:
+        s0 = sessions[0]
+        s0.set_profiling(True)
+        tc_ms, tc_gf, n_prof = 0.0, 0.0, 8
+        for i in range(n_prof):
+            body.submit((frames_dev[i].data_ptr(), (H, W)), s0, where=1)
+            body.collect(s0)
+            for name, ms, gf in s0.profile():
+                key = name.split(":")[0]
+                stages[key] = stages.get(key, 0.0) + ms / n_prof
+                if key == "conv_tc128":
+                    tc_ms += ms
+                    tc_gf += gf
+        s0.set_profiling(False)
+        peak, hbm, how = measured_peaks()
+        achieved = tc_gf / tc_ms if tc_ms > 0 else 0.0            # GFLOP/ms == TFLOP/s
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+                traffic = json.load(f).get("conv_tc128_dram_bytes_per_frame")
+        except Exception:
+            pass
+        roof = {"bound": "tensor", "kernel": "conv_tc_kernel<128> (tcgen05 implicit-GEMM conv, all launches of one frame)",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": how,
+                "traffic": traffic, "gflop_per_frame": tc_gf / n_prof, "ms_per_frame": tc_ms / n_prof,
+                "measured_over": "%d serialised profiled frames after the timed region (CUDA events around every launch)" % n_prof}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        t = cpu_reference_frames(2, threads)
+        cpu = {"value": 2.0 / float(np.sum(t)), "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": "2 full 720p 4-scale frames through the oracle restatement of src/body.py (no warm-up)"}
+
+    if rank == 0:
+        total_frames = F * K * world
+        d2h = F * (4 * 25 + 2048 * 32 + 128 * 160)
+        line = {"metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
+                "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                "config": {"workload": "Body() 4-scale [0.5,1.0,1.5,2.0] on synthetic 1280x720 frames, random-init bodypose_model",
+                           "frames_per_step": F, "streams": len(sessions), "parallelism": "frame-sharded replicas x%d" % world,
+                           "l2": "pool of %d distinct frames (177 MB) and ~1 GB of activations per frame exceed the 126 MB L2" % POOL_FRAMES},
+                "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W * 3,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
+                "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "stage_ms_per_frame": {k: round(v, 4) for k, v in stages.items()}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--streams", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,16 @@ int opb_net_layer_info(int kind, int index, const char** name, int* cout, int* c
 int opb_session_create(opb_net* net, opb_session** out);
 int opb_session_destroy(opb_session* s);
 
+/* Measurement hooks (bench.py).  Profiling records a CUDA event after every stage / convolution launch of the
+ * next submitted frame; profile_get(i) returns the name of mark i, the device time since mark i-1 and the
+ * algorithmic GFLOP of that launch (0 for non-convolution marks).  mark/elapsed time a region on the session's
+ * own stream(s) with CUDA events.                                                                     */
+int opb_session_set_profiling(opb_session* s, int on);
+int opb_session_profile_count(opb_session* s);
+int opb_session_profile_get(opb_session* s, int i, const char** name, float* ms_since_prev, double* gflop);
+int opb_session_mark(opb_session* s, int slot);
+int opb_session_elapsed(opb_session* a, int slot_a, opb_session* b, int slot_b, float* ms);
+
 /* ---- Body.__call__ (src/body.py:24-212) --------------------------------------------------------
  * submit: enqueue the whole frame (H2D of the image when img_is_device == 0, preprocessing at every
  *         scale, CNN, upsample/average, Gaussian+NMS, PAF scoring, matching, assembly, D2H of the

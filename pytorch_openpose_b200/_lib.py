@@ -36,6 +36,11 @@ SIGNATURES = {
                                    POINTER(c_int)]),
     "opb_session_create": (c_int, [c_void_p, POINTER(c_void_p)]),
     "opb_session_destroy": (c_int, [c_void_p]),
+    "opb_session_set_profiling": (c_int, [c_void_p, c_int]),
+    "opb_session_profile_count": (c_int, [c_void_p]),
+    "opb_session_profile_get": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_float), POINTER(c_double)]),
+    "opb_session_mark": (c_int, [c_void_p, c_int]),
+    "opb_session_elapsed": (c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(c_float)]),
     "opb_body_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_double), c_int]),
     "opb_body_wait": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "opb_body_fetch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int]),
@@ -172,6 +177,27 @@ class Session(object):
         self.net = net
         self.handle = c_void_p()
         check(lib().opb_session_create(net.handle, ctypes.byref(self.handle)))
+
+    def set_profiling(self, on):
+        check(lib().opb_session_set_profiling(self.handle, int(on)))
+
+    def profile(self):
+        """[(mark name, ms since previous mark, algorithmic GFLOP)] of the last profiled frame."""
+        L = lib()
+        out = []
+        for i in range(L.opb_session_profile_count(self.handle)):
+            name, ms, gf = c_char_p(), c_float(), c_double()
+            check(L.opb_session_profile_get(self.handle, i, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(gf)))
+            out.append((name.value.decode(), ms.value, gf.value))
+        return out
+
+    def mark(self, slot):
+        check(lib().opb_session_mark(self.handle, slot))
+
+    def elapsed_ms(self, slot_a, other, slot_b):
+        ms = c_float()
+        check(lib().opb_session_elapsed(self.handle, slot_a, other.handle, slot_b, ctypes.byref(ms)))
+        return ms.value
 
     def __del__(self):
         try:

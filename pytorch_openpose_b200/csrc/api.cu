@@ -174,6 +174,8 @@ struct opb_session {
     std::vector<double> cand_all, subset_all;   // filled by wait() when the eager copy was too small
     int n_cand = 0, n_subset = 0, status = 0;
     int hand_crops = 0;
+    Profiler prof;
+    cudaEvent_t marks[2] = {nullptr, nullptr};
     // stage-level net plans (opb_net_forward)
     std::map<std::vector<NetShape>, std::unique_ptr<NetPlan>> net_plans;
     ~opb_session() {
@@ -182,6 +184,7 @@ struct opb_session {
         if (host) cudaFreeHost(host);
         if (staging) cudaFreeHost(staging);
         if (done) cudaEventDestroy(done);
+        for (auto m : marks) if (m) cudaEventDestroy(m);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -264,7 +267,8 @@ static void run_front(opb_session* s, FramePlan* fp, int n, int H, int W) {
         const U8Taps& t = fp->u8taps[i];
         preprocess_launch_batched(fp->d_img, n, H, W, fp->net->in_u8[i], d.h, d.w, d.hp, d.wp, t.xf, t.xc, t.yf, t.yc, st);
     }
-    fp->net->run(st);
+    s->prof.mark(st, "preprocess");
+    fp->net->run(st, s->prof.on ? &s->prof : nullptr);
 }
 
 static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int H, int W, float* out, cudaStream_t st) {
@@ -290,14 +294,21 @@ static void body_submit(opb_session* s, const uint8_t* img, int where, int H, in
     ensure_host(s, 0);
     s->active = fp;
     cudaStream_t st = s->stream;
+    s->prof.reset();
+    s->prof.mark(st, "start");
     upload_image(s, fp, img, where, (size_t)H * W * 3);
+    s->prof.mark(st, "h2d");
     run_front(s, fp, 1, H, W);
     run_upsample(fp, false, 1, 19, 24, H, W, fp->heat_avg, st);
     run_upsample(fp, true, 1, 38, 40, H, W, fp->paf_avg, st);
+    s->prof.mark(st, "upsample_avg");
     smooth_nms_launch(fp->heat_avg, H, W, 18, 0.1, fp->pb, nullptr, st);            // thre1, src/body.py:30
+    s->prof.mark(st, "smooth_nms");
     sort_peaks_launch2(fp->pb, 18, fp->part_count, st);
+    s->prof.mark(st, "sort_peaks");
     paf_group_launch2(fp->paf_avg, H, W, fp->pb.candidates, fp->pb.part_begin, fp->lb, 0.05, fp->order, fp->used,
                       fp->pb.capacity, st);                                          // thre2, src/body.py:31
+    s->prof.mark(st, "paf_group");
     HostResults* h = s->host;
     OPB_CUDA(cudaMemcpyAsync(&h->counts[0], fp->pb.count, sizeof(int), cudaMemcpyDeviceToHost, st));
     OPB_CUDA(cudaMemcpyAsync(&h->counts[1], fp->pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -305,6 +316,7 @@ static void body_submit(opb_session* s, const uint8_t* img, int where, int H, in
     OPB_CUDA(cudaMemcpyAsync(&h->counts[21], fp->lb.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     OPB_CUDA(cudaMemcpyAsync(h->cand, fp->pb.candidates, sizeof(h->cand), cudaMemcpyDeviceToHost, st));
     OPB_CUDA(cudaMemcpyAsync(h->subset, fp->lb.subset, sizeof(h->subset), cudaMemcpyDeviceToHost, st));
+    s->prof.mark(st, "d2h");
     OPB_CUDA(cudaEventRecord(s->done, st));
     s->net->ctx->launches += fp->launches_per_frame;
 }
@@ -352,11 +364,17 @@ static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, in
     s->active = fp;
     s->hand_crops = n;
     cudaStream_t st = s->stream;
+    s->prof.reset();
+    s->prof.mark(st, "start");
     upload_image(s, fp, img, where, (size_t)n * H * W * 3);
+    s->prof.mark(st, "h2d");
     run_front(s, fp, n, H, W);
     run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);
+    s->prof.mark(st, "upsample_avg");
     hand_peaks_launch2(fp->heat_avg, n, 22, H, W, 0.03, fp->hb, nullptr, st);        // thre, src/hand.py:31
+    s->prof.mark(st, "hand_peaks");
     OPB_CUDA(cudaMemcpyAsync(s->host->hand_peaks, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    s->prof.mark(st, "d2h");
     OPB_CUDA(cudaEventRecord(s->done, st));
     s->net->ctx->launches += fp->launches_per_frame;
 }
@@ -497,6 +515,43 @@ int opb_body_fetch(opb_session* s, double* candidate, int cand_rows, double* sub
             const double* src = s->subset_all.empty() ? s->host->subset : s->subset_all.data();
             memcpy(subset, src, (size_t)s->n_subset * 20 * sizeof(double));
         }
+    });
+}
+
+int opb_session_set_profiling(opb_session* s, int on) {
+    return guarded([&] {
+        OPB_REQUIRE(s != nullptr, "null session");
+        s->prof.on = on != 0;
+        s->prof.reset();
+    });
+}
+int opb_session_profile_count(opb_session* s) { return s ? (int)s->prof.used : 0; }
+int opb_session_profile_get(opb_session* s, int i, const char** name, float* ms_since_prev, double* gflop) {
+    return guarded([&] {
+        OPB_REQUIRE(s && i >= 0 && i < (int)s->prof.used, "profile index out of range");
+        OPB_CUDA(cudaEventSynchronize(s->prof.ev[i]));
+        float ms = 0.f;
+        if (i > 0) OPB_CUDA(cudaEventElapsedTime(&ms, s->prof.ev[i - 1], s->prof.ev[i]));
+        if (name) *name = s->prof.names[i].c_str();
+        if (ms_since_prev) *ms_since_prev = ms;
+        if (gflop) *gflop = s->prof.gflop[i];
+    });
+}
+/* timing marks on the session's stream (bench.py): slot 0/1 */
+int opb_session_mark(opb_session* s, int slot) {
+    return guarded([&] {
+        OPB_REQUIRE(s && slot >= 0 && slot < 2, "slot 0 or 1");
+        OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+        if (!s->marks[slot]) OPB_CUDA(cudaEventCreate(&s->marks[slot]));
+        OPB_CUDA(cudaEventRecord(s->marks[slot], s->stream));
+    });
+}
+int opb_session_elapsed(opb_session* a, int slot_a, opb_session* b, int slot_b, float* ms) {
+    return guarded([&] {
+        OPB_REQUIRE(a && b && ms && a->marks[slot_a] && b->marks[slot_b], "marks not recorded");
+        OPB_CUDA(cudaEventSynchronize(a->marks[slot_a]));
+        OPB_CUDA(cudaEventSynchronize(b->marks[slot_b]));
+        OPB_CUDA(cudaEventElapsedTime(ms, a->marks[slot_a], b->marks[slot_b]));
     });
 }
 

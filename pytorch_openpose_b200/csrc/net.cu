@@ -227,9 +227,12 @@ struct Builder {
         while (i < names.size()) {
             std::vector<ConvOp> ops;
             const int bn = net->dev.at(names[i]).block_n;
+            const size_t first = i;
+            double gf = 0;
             for (; i < names.size() && (int)ops.size() < kConvMaxProblems; ++i) {
                 const DevLayer& d = net->dev.at(names[i]);
                 if (d.block_n != bn) break;
+                gf += add_flops(names[i], ins[i]);
                 ConvOp op;
                 op.in = ins[i];
                 op.out = outs[i];
@@ -246,12 +249,20 @@ struct Builder {
             ConvLaunch* L = conv_tc_plan(ops, bn, net->ctx->num_sms);
             plan->launches.push_back(L);
             plan->steps.push_back([L](cudaStream_t s) { conv_tc_plan_run(L, s); });
+            plan->step_names.push_back(std::string(bn == 128 ? "conv_tc128:" : "conv_tc64:") + names[first]);
+            plan->step_gflop.push_back(gf);
             plan->kernel_launches += 1;
         }
     }
-    void add_flops(const std::string& name, const TensorView& in) {
+    // algorithmic FLOPs of one layer on one input (un-padded channel counts)
+    double add_flops(const std::string& name, const TensorView& in) {
         for (const auto& s : layer_specs(net->kind))
-            if (s.name == name) plan->gflop += 2.0 * s.cout * s.cin * s.k * s.k * (double)in.pixels() * 1e-9;
+            if (s.name == name) {
+                const double gf = 2.0 * s.cout * s.cin * s.k * s.k * (double)in.pixels() * 1e-9;
+                plan->gflop += gf;
+                return gf;
+            }
+        return 0.0;
     }
 };
 
@@ -276,8 +287,9 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
         TensorView out = B.act(sh.n, sh.hp, sh.wp, 64);
         const DevLayer& d = net->dev.at("conv1_1");
         plan->steps.push_back([in, out, d](cudaStream_t st) { conv_first_launch(in, out, d.w_first, d.bias, st); });
+        plan->step_names.push_back("conv_first:conv1_1");
+        plan->step_gflop.push_back(B.add_flops("conv1_1", in));
         plan->kernel_launches += 1;
-        B.add_flops("conv1_1", in);
         cur[s] = out;
     }
 
@@ -285,7 +297,6 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
     auto trunk = [&](const std::string& name, int cout, bool pool, std::vector<TensorView>* into = nullptr) {
         std::vector<TensorView> outs(S);
         for (int s = 0; s < S; ++s) {
-            B.add_flops(name, cur[s]);
             if (into)
                 outs[s] = (*into)[s];
             else if (pool && B.fuse_pool)
@@ -299,6 +310,8 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
                 TensorView pooled = B.act(outs[s].n, outs[s].h / 2, outs[s].w / 2, cout);
                 TensorView full = outs[s];
                 plan->steps.push_back([full, pooled](cudaStream_t st) { maxpool2_launch(full, pooled, st); });
+                plan->step_names.push_back("maxpool2");
+                plan->step_gflop.push_back(0.0);
                 plan->kernel_launches += 1;
                 outs[s] = pooled;
             }
@@ -350,7 +363,6 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
                     if (two_args) snprintf(buf, sizeof buf, fmt, stage, b + 1);
                     else snprintf(buf, sizeof buf, fmt, b + 1);
                     names[2 * s + b] = buf;
-                    B.add_flops(buf, ins[2 * s + b]);
                 }
             // problems of one launch must share block_n: group by branch when they differ
             std::vector<std::string> n1, n2;
@@ -423,7 +435,6 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
             wide[s] = B.act(cat[s].n, cat[s].h, cat[s].w, 512);
         }
         auto layer = [&](const std::string& name, const std::vector<TensorView>& ins, const std::vector<TensorView>& outs) {
-            for (int s = 0; s < S; ++s) B.add_flops(name, ins[s]);
             B.conv_group(std::vector<std::string>(S, name), ins, outs, false);
         };
         layer("conv6_1_CPM", feat, wide);

@@ -77,17 +77,46 @@ struct NetShape {
         return n != o.n ? n < o.n : (hp != o.hp ? hp < o.hp : wp < o.wp);
     }
 };
+// per-step CUDA-event profiler (bench.py roofline numbers; off by default)
+struct Profiler {
+    bool on = false;
+    std::vector<cudaEvent_t> ev;
+    std::vector<std::string> names;
+    std::vector<double> gflop;
+    size_t used = 0;
+    void reset() { used = 0; names.clear(); gflop.clear(); }
+    void mark(cudaStream_t st, const std::string& name, double gf = 0.0) {
+        if (!on) return;
+        if (used == ev.size()) {
+            cudaEvent_t e;
+            OPB_CUDA(cudaEventCreate(&e));
+            ev.push_back(e);
+        }
+        OPB_CUDA(cudaEventRecord(ev[used++], st));
+        names.push_back(name);
+        gflop.push_back(gf);
+    }
+    ~Profiler() {
+        for (auto e : ev) cudaEventDestroy(e);
+    }
+};
+
 struct NetPlan {
     DevPool pool;
     std::vector<NetShape> shapes;
     std::vector<uint8_t*> in_u8;                // per scale: (n, hp, wp, 3) uint8 input
     std::vector<float*> out_paf, out_heat;      // per scale: fp32 NHWC (cstride 40 / 24); hand: heat only
     std::vector<std::function<void(cudaStream_t)>> steps;
+    std::vector<std::string> step_names;        // parallel to steps
+    std::vector<double> step_gflop;
     std::vector<ConvLaunch*> launches;
     int kernel_launches = 0;
     double gflop = 0;                           // algorithmic FLOPs (un-padded channels), for the roofline
-    void run(cudaStream_t s) const {
-        for (auto& f : steps) f(s);
+    void run(cudaStream_t s, Profiler* prof = nullptr) const {
+        for (size_t i = 0; i < steps.size(); ++i) {
+            steps[i](s);
+            if (prof) prof->mark(s, step_names[i], step_gflop[i]);
+        }
     }
     ~NetPlan();
 };
