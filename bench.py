@@ -225,6 +225,16 @@ def run_ours(args):
                     tc_ms += ms
                     tc_gf += gf
         s0.set_profiling(False)
+        if args.layers:
+            per = {}
+            for name, ms, gf in s0.profile():
+                a = per.setdefault(name, [0.0, 0.0])
+                a[0] += ms
+                a[1] += gf
+            with open(args.layers, "w") as f:
+                f.write("step,ms,gflop,tflops\n")
+                for name, (ms, gf) in per.items():
+                    f.write("%s,%.4f,%.2f,%.1f\n" % (name, ms, gf, gf / ms if ms > 0 else 0.0))
         peak, hbm, how = measured_peaks()
         achieved = tc_gf / tc_ms if tc_ms > 0 else 0.0            # GFLOP/ms == TFLOP/s
         traffic = None
@@ -272,6 +282,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=16)
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--layers", default=None, help="write the per-launch profile of one frame to this CSV")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

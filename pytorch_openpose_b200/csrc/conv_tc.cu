@@ -21,6 +21,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer (1 lane), warp 1 = TMEM owner + MMA issuer (1 lane),
 // warps 2..5 = epilogue (TMEM lane quadrant = warp_idx % 4).
 #include "opb_common.cuh"
+#include "tc_ptx.cuh"
 
 namespace opb {
 namespace {
@@ -66,119 +67,7 @@ struct Cfg {
     static constexpr int kSmemBytes = 1024 /*align slack*/ + kStages * kStageBytes + kBarBytes + kBiasBytes;
 };
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ uint32_t mbar_try_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.b32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok;
-}
-// A wait that cannot hang the GPU: a pipeline bug (bad tensor map, wrong byte count) traps after ~2 s
-// instead of spinning until the watchdog.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > (1ll << 32)) {
-            printf("opb conv_tc: mbarrier timeout (tag %d, block %d, thread %d)\n", tag, (int)blockIdx.x,
-                   (int)threadIdx.x);
-            __trap();
-        }
-    }
-}
-__device__ __forceinline__ void fence_barrier_init() {
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1,
-                                            int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* tm) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(tm) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
-                 "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                          uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// arrives on the mbarrier once every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major SWIZZLE_128B shared-memory matrix descriptor: rows of 128 B, 8-row groups 1024 B apart.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-    uint64_t d = 0;
-    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);      // [0,14)  start address >> 4
-    d |= (uint64_t)1 << 16;                        // [16,30) leading byte offset >> 4 (unused for SW128 K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;              // [32,46) stride byte offset >> 4
-    d |= (uint64_t)1 << 46;                        // [46,48) descriptor version = 1 (sm_100)
-    d |= (uint64_t)2 << 61;                        // [61,64) layout = SWIZZLE_128B
-    return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-}
+using namespace tc;
 
 struct TileCoord {
     int pi, img, x0, y0, n0;
@@ -220,7 +109,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + kAccStages);
     float* sbias = (float*)((uint8_t*)full_bar + C::kBarBytes);
 
-    const int warp = threadIdx.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);      // warp-uniform role index
     const int lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -242,14 +131,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    // broadcast so the compiler knows the TMEM base is warp-uniform (keeps UTCHMMA operands in uniform registers)
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
     const int taps = p.ks * p.ks;
     const int pad = p.ks >> 1;
 
     if (warp == 0) {
         // ================= TMA producer =================
-        if (lane == 0) {
+        {   // all 32 lanes walk the loop (warp-uniform); one elected lane issues each async op
             int stage = 0;
             uint32_t phase = 0;
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
@@ -264,9 +154,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         mbar_wait(&empty_bar[stage], phase ^ 1, 0);
                         uint8_t* a_dst = tiles + stage * C::kStageBytes;
                         uint8_t* b_dst = a_dst + kABytes;
-                        mbar_arrive_expect_tx(&full_bar[stage], C::kStageBytes);
-                        tma_load_4d(a_dst, tmA, &full_bar[stage], cc * kBlockK, tc.x0 + dx, tc.y0 + dy, tc.img);
-                        tma_load_2d(b_dst, tmW, &full_bar[stage], (tap * cin_chunks + cc) * kBlockK, tc.n0);
+                        mbar_arrive_expect_tx_elect(&full_bar[stage], C::kStageBytes);
+                        tma_load_4d_elect(a_dst, tmA, &full_bar[stage], cc * kBlockK, tc.x0 + dx, tc.y0 + dy, tc.img);
+                        tma_load_2d_elect(b_dst, tmW, &full_bar[stage], (tap * cin_chunks + cc) * kBlockK, tc.n0);
                         if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -274,7 +164,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        {   // all 32 lanes walk the loop (warp-uniform); one elected lane issues each async op
             constexpr uint32_t idesc = make_idesc(BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
@@ -295,12 +185,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // +32 bytes per K=16 step inside the 128-byte swizzle row: +2 in the >>4 address field
-                        umma_bf16(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16_elect(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);                  // smem slot reusable once these MMAs retire
+                    umma_commit_elect(&empty_bar[stage]);                  // smem slot reusable once these MMAs retire
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(&tfull_bar[acc]);                        // accumulator complete -> epilogue
+                umma_commit_elect(&tfull_bar[acc]);                        // accumulator complete -> epilogue
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -416,8 +306,10 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
-void encode(CUtensorMap* tm, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-            const cuuint32_t* box) {
+}  // namespace
+
+void tensor_map_encode_bf16(CUtensorMap* tm, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                            const cuuint32_t* box) {
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     OPB_REQUIRE(((uintptr_t)addr & 15) == 0, "TMA base address must be 16-byte aligned");
     CUresult r = encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, addr, dims, strides, box, estr,
@@ -425,6 +317,8 @@ void encode(CUtensorMap* tm, void* addr, int rank, const cuuint64_t* dims, const
                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error(OPB_ERR_CUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
 }
+
+namespace {
 
 // tile = tw x th output pixels with tw*th = 128; pick the shape that wastes the fewest pixels
 int choose_tw_log2(int H, int W, bool pool) {
@@ -444,13 +338,14 @@ int choose_tw_log2(int H, int W, bool pool) {
 
 }  // namespace
 
-struct ConvLaunch {
+struct TapLaunch : ConvLaunch {
     ConvParams params;
     int grid = 0;
     int block_n = 128;
+    void run(cudaStream_t stream) const override;
 };
 
-static void conv_tc_prepare(const std::vector<ConvOp>& ops, int block_n, int num_sms, ConvLaunch& L) {
+static void conv_tc_prepare(const std::vector<ConvOp>& ops, int block_n, int num_sms, TapLaunch& L) {
     OPB_REQUIRE(!ops.empty() && (int)ops.size() <= kConvMaxProblems, "conv_tc: 1..8 problems per launch");
     OPB_REQUIRE(block_n == 64 || block_n == 128, "conv_tc: block_n must be 64 or 128");
     ConvParams& P = L.params;
@@ -498,20 +393,21 @@ static void conv_tc_prepare(const std::vector<ConvOp>& ops, int block_n, int num
         cuuint64_t astr[3] = {(cuuint64_t)op.in.cstride * 2, (cuuint64_t)op.in.cstride * 2 * W,
                               (cuuint64_t)op.in.cstride * 2 * W * H};
         cuuint32_t abox[4] = {(cuuint32_t)kBlockK, (cuuint32_t)tw, (cuuint32_t)th, 1};
-        encode(&P.tmA[i], op.in.ptr(), 4, adims, astr, abox);
+        tensor_map_encode_bf16(&P.tmA[i], op.in.ptr(), 4, adims, astr, abox);
         // W: [cout_pad][K] bf16
         const cuuint64_t K = (cuuint64_t)op.ks * op.ks * op.in.c;
         cuuint64_t wdims[2] = {K, (cuuint64_t)op.cout_pad};
         cuuint64_t wstr[1] = {K * 2};
         cuuint32_t wbox[2] = {(cuuint32_t)kBlockK, (cuuint32_t)block_n};
-        encode(&P.tmW[i], (void*)op.w, 2, wdims, wstr, wbox);
+        tensor_map_encode_bf16(&P.tmW[i], (void*)op.w, 2, wdims, wstr, wbox);
     }
     P.total_tiles = tile;
+    L.tiles = tile;
     L.block_n = block_n;
     L.grid = tile < num_sms ? tile : num_sms;
 }
 
-static void conv_tc_run(const ConvLaunch& L, cudaStream_t stream) {
+static void conv_tc_run(const TapLaunch& L, cudaStream_t stream) {
     static bool attr_set = false;
     if (!attr_set) {
         OPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -527,23 +423,16 @@ static void conv_tc_run(const ConvLaunch& L, cudaStream_t stream) {
     OPB_CUDA(cudaGetLastError());
 }
 
-// opaque handle API used by net.cu (keeps ConvParams out of the shared header)
+void TapLaunch::run(cudaStream_t stream) const { conv_tc_run(*this, stream); }
+
 ConvLaunch* conv_tc_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms) {
-    ConvLaunch* L = new ConvLaunch();
-    try {
-        conv_tc_prepare(ops, block_n, num_sms, *L);
-    } catch (...) {
-        delete L;
-        throw;
-    }
-    return L;
+    auto L = std::make_unique<TapLaunch>();
+    conv_tc_prepare(ops, block_n, num_sms, *L);
+    return L.release();
 }
-void conv_tc_plan_run(const ConvLaunch* L, cudaStream_t stream) { conv_tc_run(*L, stream); }
-void conv_tc_plan_free(ConvLaunch* L) { delete L; }
-int conv_tc_plan_tiles(const ConvLaunch* L) { return L->params.total_tiles; }
 
 void conv_tc_launch(const std::vector<ConvOp>& ops, int block_n, cudaStream_t stream, int num_sms) {
-    ConvLaunch L;
+    TapLaunch L;
     conv_tc_prepare(ops, block_n, num_sms, L);
     conv_tc_run(L, stream);
 }

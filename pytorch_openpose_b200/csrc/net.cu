@@ -10,6 +10,7 @@
 #include "net.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace opb {
 
@@ -208,6 +209,7 @@ struct Builder {
     opb_net* net;
     NetPlan* plan;
     bool fuse_pool;
+    int conv_impl;          // -1: per-tap tiles everywhere, 0 / 1: patch-resident MODE 0 / 1 for ks > 1
     TensorView act(int n, int h, int w, int c, int elem = 2, bool zero = false) {
         TensorView t;
         t.n = n; t.h = h; t.w = w; t.c = c; t.cstride = c; t.coff = 0; t.elem = elem;
@@ -246,7 +248,9 @@ struct Builder {
                 OPB_REQUIRE(op.in.c == d.cin_dev, "plan: input channel mismatch for " + names[i]);
                 ops.push_back(op);
             }
-            ConvLaunch* L = conv_tc_plan(ops, bn, net->ctx->num_sms);
+            // 3x3 / 7x7 layers run patch-resident (conv_patch.cu); 1x1 layers (and OPB_CONV_IMPL=tap) per-tap tiles
+            ConvLaunch* L = (ops[0].ks > 1 && conv_impl >= 0) ? conv_patch_plan(ops, bn, net->ctx->num_sms, conv_impl)
+                                                             : conv_tc_plan(ops, bn, net->ctx->num_sms);
             plan->launches.push_back(L);
             plan->steps.push_back([L](cudaStream_t s) { conv_tc_plan_run(L, s); });
             plan->step_names.push_back(std::string(bn == 128 ? "conv_tc128:" : "conv_tc64:") + names[first]);
@@ -268,12 +272,20 @@ struct Builder {
 
 }  // namespace
 
+int default_conv_impl() {
+    const char* e = getenv("OPB_CONV_IMPL");
+    if (e && !strcmp(e, "tap")) return -1;
+    if (e && !strcmp(e, "patch0")) return 0;
+    if (e && !strcmp(e, "patch1")) return 1;
+    return kDefaultConvImpl;
+}
+
 std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape>& shapes) {
     OPB_REQUIRE(net->finalized, "net not finalized");
     OPB_REQUIRE(!shapes.empty() && (int)shapes.size() <= kMaxScales, "1..8 scales per plan");
     auto plan = std::make_unique<NetPlan>();
     plan->shapes = shapes;
-    Builder B{net, plan.get(), getenv("OPB_NO_FUSE_POOL") == nullptr};
+    Builder B{net, plan.get(), getenv("OPB_NO_FUSE_POOL") == nullptr, default_conv_impl()};
     const int S = (int)shapes.size();
     const bool body = net->kind == OPB_NET_BODY;
     std::vector<TensorView> cur(S);

@@ -122,6 +122,8 @@ struct NetPlan {
 };
 std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape>& shapes);
 void finalize_net(opb_net* net);
+constexpr int kDefaultConvImpl = 1;       // measured on B200 (bench.py, 720p 4-scale): patch MODE 1 1037 TFLOP/s, MODE 0 945, per-tap 948
+int default_conv_impl();
 
 // cubic tap tables (host)
 struct CubicTaps {

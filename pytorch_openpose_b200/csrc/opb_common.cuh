@@ -10,6 +10,8 @@
 #include <vector>
 #include <map>
 #include <stdexcept>
+#include <memory>
+#include <cstring>
 
 #include "../../include/openpose_b200.h"
 
@@ -66,11 +68,17 @@ struct ConvOp {                 // one problem of a grouped launch
 
 void conv_tc_launch(const std::vector<ConvOp>& ops, int block_n, cudaStream_t stream, int num_sms);
 // pre-encoded launch (tensor maps + tile list built once per plan, replayed per frame)
-struct ConvLaunch;
-ConvLaunch* conv_tc_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms);
-void conv_tc_plan_run(const ConvLaunch* L, cudaStream_t stream);
-void conv_tc_plan_free(ConvLaunch* L);
-int conv_tc_plan_tiles(const ConvLaunch* L);
+struct ConvLaunch {
+    int tiles = 0;
+    virtual void run(cudaStream_t stream) const = 0;
+    virtual ~ConvLaunch() {}
+};
+ConvLaunch* conv_tc_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms);               // per-tap tiles (any ks)
+ConvLaunch* conv_patch_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms, int mode);   // patch-resident (ks 3/7)
+inline void conv_tc_plan_run(const ConvLaunch* L, cudaStream_t stream) { L->run(stream); }
+inline void conv_tc_plan_free(ConvLaunch* L) { delete L; }
+void tensor_map_encode_bf16(CUtensorMap* tm, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                            const cuuint32_t* box);
 
 // ---- SIMT kernels (conv_simt.cu)
 void conv_direct_launch(const ConvOp& op, cudaStream_t stream);                   // debug / cross-check

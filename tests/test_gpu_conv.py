@@ -39,16 +39,22 @@ CASES = [
 ]
 
 
+IMPLS = {"tap": 2, "patch0": 3, "patch1": 4}       # per-tap tiles / patch-resident MODE 0 / MODE 1 (opb_conv2d impl)
+
+
+@pytest.mark.parametrize("impl", sorted(IMPLS))
 @pytest.mark.parametrize("case", CASES, ids=lambda c: "n%d_%dx%d_c%d_o%d_k%d_r%d_p%d_f%d" % tuple(int(v) for v in c))
-def test_conv_tc_matches_torch(case):
+def test_conv_tc_matches_torch(case, impl):
     from tests import gpu_util as G
     n, h, w, cin, cout, k, relu, pool, fp32 = case
+    if k == 1 and impl != "tap":
+        pytest.skip("1x1 layers always use the per-tap kernel")
     g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
     x = (torch.randn(n, h, w, cin, generator=g) * 0.5).to(torch.bfloat16).cuda()
     wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
     b = torch.randn(cout, generator=g) * 0.1
     ref = _reference(x, wt, b, relu, pool)
-    out = G.conv2d(x, wt, b, relu, pool, fp32, impl=0).float()
+    out = G.conv2d(x, wt, b, relu, pool, fp32, impl=IMPLS[impl]).float()
     assert not torch.isnan(out[..., :cout]).any(), "kernel left output elements unwritten"
     if out.shape[-1] > cout:
         assert (out[..., cout:] == 0).all(), "padded output channels must be written as zeros"
