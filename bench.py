@@ -224,7 +224,6 @@ def run_ours(args):
                 if key == "conv_tc128":
                     tc_ms += ms
                     tc_gf += gf
-        s0.set_profiling(False)
         if args.layers:
             per = {}
             for name, ms, gf in s0.profile():
@@ -235,6 +234,7 @@ def run_ours(args):
                 f.write("step,ms,gflop,tflops\n")
                 for name, (ms, gf) in per.items():
                     f.write("%s,%.4f,%.2f,%.1f\n" % (name, ms, gf, gf / ms if ms > 0 else 0.0))
+        s0.set_profiling(False)
         peak, hbm, how = measured_peaks()
         achieved = tc_gf / tc_ms if tc_ms > 0 else 0.0            # GFLOP/ms == TFLOP/s
         traffic = None

@@ -70,8 +70,11 @@ static U8Taps make_u8_taps(DevPool& pool, int H, int W, const ScaleDims& d) {
 struct UpTables {
     int *xf, *yf;
     float *xw, *yw;
+    int *ybf, *ybr;       // 16-row strip tables of the register-blocked y pass
+    float* ybw;
+    int yb_rs;
 };
-static UpTables make_up_tables(DevPool& pool, int H, int W, const ScaleDims& d) {
+static UpTables make_up_tables(DevPool& pool, int H, int W, const ScaleDims& d, int n_scales) {
     std::vector<int> fx, fy;
     std::vector<float> wx, wy;
     composite_taps(d.wo, d.w, W, fx, wx);
@@ -81,6 +84,31 @@ static UpTables make_up_tables(DevPool& pool, int H, int W, const ScaleDims& d) 
     t.yf = pool.upload(fy);
     t.xw = pool.upload(wx);
     t.yw = pool.upload(wy);
+    // strips of 16 output rows: first source row, number of source rows, dense weights (x 1/n_scales)
+    const int TY = 16, nyb = (H + TY - 1) / TY;
+    std::vector<int> bf(nyb), br(nyb);
+    int rs = 1;
+    for (int b = 0; b < nyb; ++b) {
+        int lo = d.ho, hi = -1;
+        for (int y = b * TY; y < std::min(H, (b + 1) * TY); ++y) {
+            lo = std::min(lo, fy[y]);
+            hi = std::max(hi, std::min(fy[y] + kUpTaps - 1, d.ho - 1));
+        }
+        bf[b] = lo;
+        br[b] = hi - lo + 1;
+        rs = std::max(rs, br[b]);
+    }
+    std::vector<float> bw((size_t)nyb * rs * TY, 0.f);
+    for (int b = 0; b < nyb; ++b)
+        for (int y = b * TY; y < std::min(H, (b + 1) * TY); ++y)
+            for (int k = 0; k < kUpTaps; ++k) {
+                const int r = std::min(fy[y] + k, d.ho - 1) - bf[b];      // same clamp as the generic kernel
+                bw[((size_t)b * rs + r) * TY + (y - b * TY)] += wy[(size_t)y * kUpTaps + k] / (float)n_scales;
+            }
+    t.ybf = pool.upload(bf);
+    t.ybr = pool.upload(br);
+    t.ybw = pool.upload(bw);
+    t.yb_rs = rs;
     return t;
 }
 
@@ -221,7 +249,7 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
         const ScaleDims d = scale_dims(H, W, scales[i]);
         fp->dims.push_back(d);
         fp->u8taps.push_back(make_u8_taps(fp->pool, H, W, d));
-        fp->uptabs.push_back(make_up_tables(fp->pool, H, W, d));
+        fp->uptabs.push_back(make_up_tables(fp->pool, H, W, d, n_scales));
         shapes.push_back({n, d.hp, d.wp});
         scratch += (size_t)n * C * d.ho * W;
     }
@@ -283,6 +311,10 @@ static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int
         us[i].x_w = fp->uptabs[i].xw;
         us[i].y_first = fp->uptabs[i].yf;
         us[i].y_w = fp->uptabs[i].yw;
+        us[i].yb_first = fp->uptabs[i].ybf;
+        us[i].yb_rows = fp->uptabs[i].ybr;
+        us[i].yb_w = fp->uptabs[i].ybw;
+        us[i].yb_rs = fp->uptabs[i].yb_rs;
     }
     upsample_avg_launch2(us, S, n, C, H, W, fp->up_scratch, out, st);
 }
@@ -642,8 +674,8 @@ int opb_upsample_avg(opb_context* ctx, const float* const* dev_maps, const doubl
         size_t scratch = 0;
         for (int i = 0; i < ns; ++i) {
             const ScaleDims d = scale_dims(H, W, scales[i]);
-            const UpTables t = make_up_tables(pool, H, W, d);
-            us[i] = UpsampleScale{dev_maps[i], d.ho, d.wo, cstride, t.xf, t.xw, t.yf, t.yw};
+            const UpTables t = make_up_tables(pool, H, W, d, ns);
+            us[i] = UpsampleScale{dev_maps[i], d.ho, d.wo, cstride, t.xf, t.xw, t.yf, t.yw, t.ybf, t.ybr, t.ybw, t.yb_rs};
             scratch += (size_t)C * d.ho * W;
         }
         float* tmp = pool.alloc_t<float>(scratch);

@@ -10,7 +10,9 @@
 namespace opb {
 namespace {
 
-// ---- conv1_1: one thread per output pixel, 64 output channels, weights broadcast from smem -------
+// ---- conv1_1: one thread = 4 horizontally adjacent output pixels x 64 output channels (16 at a time).  Register
+// blocking over pixels divides the shared-memory weight reads per FMA by four (the 1-pixel form was LDS-bound: ncu
+// l1tex 86 %, FMA pipe 41 %).  W is a multiple of 8 (padded image), so strips never straddle rows. ---------------
 __global__ void __launch_bounds__(128) conv_first_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                          const float* __restrict__ w /*[27][64]*/,
                                                          const float* __restrict__ bias, int N, int H, int W,
@@ -20,40 +22,66 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const uint8_t* __restri
     for (int i = threadIdx.x; i < 27 * 64; i += blockDim.x) sw[i] = w[i];
     if (threadIdx.x < 64) sb[threadIdx.x] = bias[threadIdx.x];
     __syncthreads();
-    const size_t total = (size_t)N * H * W;
-    const size_t pix = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (pix >= total) return;
-    const int x = (int)(pix % W);
-    const int y = (int)((pix / W) % H);
-    const size_t img = pix / ((size_t)W * H);
-    float v[27];
+    const int strips_per_row = W >> 2;
+    const size_t total = (size_t)N * H * strips_per_row;
+    const size_t sidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (sidx >= total) return;
+    const int x0 = (int)(sidx % strips_per_row) * 4;
+    const int y = (int)((sidx / strips_per_row) % H);
+    const size_t img = sidx / ((size_t)strips_per_row * H);
+    // 3 rows x 6 columns x 3 channels of normalised input (x/256 - 0.5 is exact in fp32; zero outside the image)
+    float v[3][6][3];
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y + dy - 1;
+        const bool rowok = (yy >= 0) && (yy < H);
+        const uint8_t* row = in + (img * H + (rowok ? yy : 0)) * (size_t)W * 3;
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-            const int yy = y + dy - 1, xx = x + dx - 1;
-            const bool ok = (yy >= 0) && (yy < H) && (xx >= 0) && (xx < W);
-            const uint8_t* p = in + ((img * H + (ok ? yy : 0)) * W + (ok ? xx : 0)) * 3;
+        for (int dx = 0; dx < 6; ++dx) {
+            const int xx = x0 + dx - 1;
+            const bool ok = rowok && (xx >= 0) && (xx < W);
+            const uint8_t* p = row + (ok ? xx : 0) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
-                v[(dy * 3 + dx) * 3 + c] = ok ? ((float)p[c] * (1.0f / 256.0f) - 0.5f) : 0.0f;   // exact in fp32
+            for (int c = 0; c < 3; ++c) v[dy][dx][c] = ok ? ((float)p[c] * (1.0f / 256.0f) - 0.5f) : 0.0f;
         }
     }
-    __nv_bfloat16* o = out + pix * out_cstride;
+    __nv_bfloat16* o = out + ((img * H + y) * (size_t)W + x0) * out_cstride;
 #pragma unroll 1
-    for (int c0 = 0; c0 < 64; c0 += 8) {
-        float acc[8];
+    for (int c16 = 0; c16 < 4; ++c16) {
+        float acc[4][16];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = sb[c0 + j];
+        for (int p = 0; p < 4; ++p)
 #pragma unroll
-        for (int k = 0; k < 27; ++k) {
+            for (int j = 0; j < 16; ++j) acc[p][j] = sb[c16 * 16 + j];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[k], sw[k * 64 + c0 + j], acc[j]);
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float* wk = &sw[((dy * 3 + dx) * 3 + c) * 64 + c16 * 16];
+                    float wv[16];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float4 t = *(const float4*)(wk + q * 4);
+                        wv[q * 4] = t.x; wv[q * 4 + 1] = t.y; wv[q * 4 + 2] = t.z; wv[q * 4 + 3] = t.w;
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p)
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[p][j] = fmaf(v[dy][dx + p][c], wv[j], acc[p][j]);
+                }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+#pragma unroll
+            for (int h8 = 0; h8 < 2; ++h8) {
+                __nv_bfloat162 h[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    h[j] = __floats2bfloat162_rn(fmaxf(acc[p][h8 * 8 + 2 * j], 0.f), fmaxf(acc[p][h8 * 8 + 2 * j + 1], 0.f));
+                *(uint4*)(o + (size_t)p * out_cstride + c16 * 16 + h8 * 8) = *(uint4*)h;
+            }
         }
-        __nv_bfloat162 h[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) h[j] = __floats2bfloat162_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-        *(uint4*)(o + c0) = *(uint4*)h;
     }
 }
 
@@ -131,7 +159,8 @@ void conv_first_launch(const TensorView& in_u8, const TensorView& out, const flo
                        cudaStream_t stream) {
     OPB_REQUIRE(in_u8.elem == 1 && in_u8.c == 3 && in_u8.cstride == 3, "conv_first: input must be dense u8 HWC3");
     OPB_REQUIRE(out.elem == 2 && out.c == 64 && out.cstride % 8 == 0 && out.coff == 0, "conv_first: output bf16 64ch");
-    const size_t total = in_u8.pixels();
+    OPB_REQUIRE(in_u8.w % 4 == 0, "conv_first: padded width must be a multiple of 4");
+    const size_t total = in_u8.pixels() / 4;                   // one thread per 4-pixel strip
     conv_first_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(
         (const uint8_t*)in_u8.base, (__nv_bfloat16*)out.base, w27x64, bias, in_u8.n, in_u8.h, in_u8.w, out.cstride);
     OPB_CUDA(cudaGetLastError());

@@ -39,9 +39,24 @@ __global__ void __launch_bounds__(256) hand_smooth_kernel(const float* __restric
     const float* map = heat + ((size_t)crop * chan_stride_maps + part) * h * w;
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int tid = threadIdx.x;
-    for (int i = tid; i < RAW_H * RAW_W; i += blockDim.x) {
-        const int ry = i / RAW_W, rx = i - ry * RAW_W;
-        raw[ry][rx] = (double)map[(size_t)reflect_idx(y0 - R + ry, h) * w + reflect_idx(x0 - R + rx, w)];
+    __shared__ int s_row[RAW_H], s_col[RAW_W];
+    if (tid < RAW_H) s_row[tid] = reflect_idx(y0 - R + tid, h);
+    else if (tid < RAW_H + RAW_W) s_col[tid - RAW_H] = reflect_idx(x0 - R + (tid - RAW_H), w);
+    __syncthreads();
+    {
+        constexpr int PER = (RAW_H * RAW_W + 255) / 256;       // batch the halo loads (memory-level parallelism)
+        float vals[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = tid + j * 256;
+            const int ry = i / RAW_W, rx = i - ry * RAW_W;
+            vals[j] = i < RAW_H * RAW_W ? __ldg(map + (size_t)s_row[ry] * w + s_col[rx]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = tid + j * 256;
+            if (i < RAW_H * RAW_W) raw[i / RAW_W][i % RAW_W] = (double)vals[j];
+        }
     }
     __syncthreads();
     for (int i = tid; i < TH * RAW_W; i += blockDim.x) {

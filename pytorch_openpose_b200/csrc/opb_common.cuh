@@ -101,6 +101,11 @@ struct UpsampleScale {
     const float* x_w;         // [W][6] composite weights
     const int* y_first;       // [H]
     const float* y_w;         // [H][6]
+    // optional 16-row strip tables for the register-blocked y pass (null -> generic kernel)
+    const int* yb_first = nullptr;     // [ceil(H/16)]
+    const int* yb_rows = nullptr;      // [ceil(H/16)]
+    const float* yb_w = nullptr;       // [ceil(H/16)][yb_rs][16], 1/n_scales folded in
+    int yb_rs = 0;
 };
 constexpr int kUpTaps = 6;
 constexpr int kMaxScales = 8;

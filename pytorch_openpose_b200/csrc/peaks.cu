@@ -30,7 +30,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
     return i >= n ? period - 1 - i : i;
 }
 
-__global__ void __launch_bounds__(256) smooth_nms_kernel(const float* __restrict__ heat, int H, int W,
+__global__ void __launch_bounds__(128, 5) smooth_nms_kernel(const float* __restrict__ heat, int H, int W,
                                                          const GaussTaps taps, double thre, PeakBuffers pb,
                                                          double* __restrict__ smoothed_out) {
     __shared__ double raw[RAW_H][RAW_W];
@@ -43,44 +43,83 @@ __global__ void __launch_bounds__(256) smooth_nms_kernel(const float* __restrict
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
     const int tid = threadIdx.x;
 
+    // reflected source row / column of every halo line, computed once per CTA (the modulo is expensive)
+    __shared__ int s_row[RAW_H], s_col[RAW_W];
+    if (tid < RAW_H) s_row[tid] = reflect_idx(y0 - 1 - R + tid, H);
+    else if (tid < RAW_H + RAW_W) s_col[tid - RAW_H] = reflect_idx(x0 - 1 - R + (tid - RAW_H), W);
     if (tid == 0) any_above = 0;
     __syncthreads();
     // The taps are positive and sum to one, so a smoothed value cannot exceed the raw maximum of its window
     // (up to ~1e-15 relative rounding): a tile whose whole halo window stays 1e-6 below thre has no peak.
     const double skip_below = thre > 0 ? thre * 0.999999 : thre * 1.000001;
     bool above = false;
-    for (int i = tid; i < RAW_H * RAW_W; i += blockDim.x) {
-        const int ry = i / RAW_W, rx = i - ry * RAW_W;
-        const float v = map[(size_t)reflect_idx(y0 - 1 - R + ry, H) * W + reflect_idx(x0 - 1 - R + rx, W)];
-        raw[ry][rx] = (double)v;
-        above |= !((double)v < skip_below);                    // NaN counts as "above": never skipped
+    {
+        // batch the halo loads (all issued before the first use) -- one-at-a-time loads left the kernel waiting on
+        // global-memory latency (ncu: long-scoreboard stalls, fp64 pipe 3.5 % busy)
+        constexpr int PER = (RAW_H * RAW_W + 127) / 128;       // 20 elements per thread at 128 threads
+        float vals[PER];
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = tid + j * 128;
+            const int ry = i / RAW_W, rx = i - ry * RAW_W;
+            vals[j] = i < RAW_H * RAW_W ? __ldg(map + (size_t)s_row[ry] * W + s_col[rx]) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < PER; ++j) {
+            const int i = tid + j * 128;
+            if (i < RAW_H * RAW_W) {
+                const int ry = i / RAW_W, rx = i - ry * RAW_W;
+                raw[ry][rx] = (double)vals[j];
+                above |= !((double)vals[j] < skip_below);          // NaN counts as "above": never skipped
+            }
+        }
     }
     if (above) any_above = 1;
     __syncthreads();
     if (!any_above && smoothed_out == nullptr) return;
 
-    // vertical pass (scipy axis 0) for the SM_H rows x RAW_W columns that the horizontal pass needs
-    for (int i = tid; i < SM_H * RAW_W; i += blockDim.x) {
-        const int r = i / RAW_W, c = i - r * RAW_W;
-        double acc = __dmul_rn(raw[r + R][c], taps.w[0]);
+    // Both passes are register-blocked: a thread pulls a run of 9+24 inputs into registers once and produces 9
+    // outputs from it (the naive form re-reads two shared-memory doubles per tap and is LDS-bound, not fp64-bound).
+    // vertical pass (scipy axis 0): SM_H = 18 rows x RAW_W = 58 columns; thread = (column, half of the rows)
+    constexpr int RUN = 9;
+    if (tid < 2 * RAW_W) {
+        const int c = tid % RAW_W, r0 = (tid / RAW_W) * RUN;
+        double v[RUN + 2 * R];
 #pragma unroll
-        for (int d = R; d >= 1; --d)
-            acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(raw[r + R - d][c], raw[r + R + d][c]), taps.w[d]));
-        ver[r][c] = acc;
+        for (int i = 0; i < RUN + 2 * R; ++i) v[i] = raw[r0 + i][c];
+#pragma unroll
+        for (int o = 0; o < RUN; ++o) {
+            double acc = __dmul_rn(v[o + R], taps.w[0]);
+#pragma unroll
+            for (int d = R; d >= 1; --d) acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + R - d], v[o + R + d]), taps.w[d]));
+            ver[r0 + o][c] = acc;
+        }
     }
     __syncthreads();
-    // horizontal pass (scipy axis 1); positions outside the image are the NMS zero border
-    for (int i = tid; i < SM_H * SM_W; i += blockDim.x) {
-        const int r = i / SM_W, c = i - r * SM_W;
-        const int y = y0 - 1 + r, x = x0 - 1 + c;
-        double acc = 0.0;
-        if (y >= 0 && y < H && x >= 0 && x < W) {
-            acc = __dmul_rn(ver[r][c + R], taps.w[0]);
+    // horizontal pass (scipy axis 1): 18 rows x 34 columns; thread = (row, run of <= 5 columns); positions outside the
+    // image are the NMS zero border
+    constexpr int RUNH = 5, NSEG = 7;                              // 7 runs of 5 columns cover the 34 columns
+    if (tid < SM_H * NSEG) {
+        const int r = tid / NSEG, seg = tid - r * NSEG;
+        const int c0 = seg * RUNH;
+        const int y = y0 - 1 + r;
+        double v[RUNH + 2 * R];
 #pragma unroll
-            for (int d = R; d >= 1; --d)
-                acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ver[r][c + R - d], ver[r][c + R + d]), taps.w[d]));
+        for (int i = 0; i < RUNH + 2 * R; ++i) v[i] = c0 + i < RAW_W ? ver[r][c0 + i] : 0.0;
+#pragma unroll
+        for (int o = 0; o < RUNH; ++o) {
+            const int c = c0 + o;
+            if (c >= SM_W) break;
+            const int x = x0 - 1 + c;
+            double acc = 0.0;
+            if (y >= 0 && y < H && x >= 0 && x < W) {
+                acc = __dmul_rn(v[o + R], taps.w[0]);
+#pragma unroll
+                for (int d = R; d >= 1; --d)
+                    acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(v[o + R - d], v[o + R + d]), taps.w[d]));
+            }
+            sm[r][c] = acc;
         }
-        sm[r][c] = acc;
     }
     __syncthreads();
 
@@ -155,7 +194,7 @@ void smooth_nms_launch(const float* heat_planar, int H, int W, int parts, double
     OPB_REQUIRE(H < (1 << 20) && W < (1 << 20), "smooth_nms: image too large for the key packing");
     OPB_CUDA(cudaMemsetAsync(pb.count, 0, sizeof(int), stream));
     dim3 grid(cdiv(W, TW), cdiv(H, TH), parts);
-    smooth_nms_kernel<<<grid, 256, 0, stream>>>(heat_planar, H, W, gauss_taps_sigma3(), thre, pb, smoothed_out);
+    smooth_nms_kernel<<<grid, 128, 0, stream>>>(heat_planar, H, W, gauss_taps_sigma3(), thre, pb, smoothed_out);
     OPB_CUDA(cudaGetLastError());
 }
 

@@ -68,23 +68,34 @@ __global__ void preprocess_kernel(const uint8_t* __restrict__ img, int H, int W,
 }
 
 // pass 1: tmp[c][r][x] = sum_k xw[x][k] * src[r][xfirst[x]+k][c]      (one scale)
+// one thread = one output column x and FOUR consecutive channels (one float4 per tap from the NHWC source)
 __global__ void upsample_x_kernel(const float* __restrict__ src, int ho, int wo, int cstride, int C, int W,
                                   const int* __restrict__ xfirst, const float* __restrict__ xw,
                                   float* __restrict__ tmp) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int r = blockIdx.y;
-    const int c = blockIdx.z;                                   // image * C + channel
+    const int cq_per_img = (C + 3) >> 2;
+    const int img = blockIdx.z / cq_per_img, cq = blockIdx.z - img * cq_per_img;
     if (x >= W) return;
-    const int img = c / C, ch = c - img * C;
     const int f = xfirst[x];
-    const float* s = src + (((size_t)img * ho + r) * wo) * cstride + ch;
-    float acc = 0.f;
+    const float* s = src + (((size_t)img * ho + r) * wo) * cstride + cq * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < kUpTaps; ++k) {
         const int col = min(f + k, wo - 1);                     // weights beyond the footprint are zero
-        acc = fmaf(xw[x * kUpTaps + k], s[(size_t)col * cstride], acc);
+        const float wk = xw[x * kUpTaps + k];
+        const float4 v = *(const float4*)(s + (size_t)col * cstride);
+        acc.x = fmaf(wk, v.x, acc.x);
+        acc.y = fmaf(wk, v.y, acc.y);
+        acc.z = fmaf(wk, v.z, acc.z);
+        acc.w = fmaf(wk, v.w, acc.w);
     }
-    tmp[((size_t)c * ho + r) * W + x] = acc;
+    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = cq * 4 + j;
+        if (ch < C) tmp[(((size_t)img * C + ch) * ho + r) * W + x] = av[j];
+    }
 }
 
 struct UpYParams {
@@ -138,6 +149,54 @@ __global__ void upsample_y_kernel(const __grid_constant__ UpYParams p, int C, in
         o[0] = acc[0];
 }
 
+// pass 2, register-blocked: one thread produces a 16-row x 4-column strip of one channel plane.  It walks the source
+// rows its strip touches once (a float4 each) and scatters them into 16 accumulators with the dense per-strip weight
+// table built on the host (1/n_scales folded in), so every scratch element is read ~2x instead of 24x.
+constexpr int kTY = 16;
+struct UpYBlocked {
+    const float* tmp[kMaxScales];
+    const int* first[kMaxScales];      // [n_yblocks]            first source row of the strip
+    const int* rows[kMaxScales];       // [n_yblocks]            source rows the strip touches
+    const float* w[kMaxScales];        // [n_yblocks][rs][16]    weight of source row r for output row yy
+    int ho[kMaxScales], rs[kMaxScales];
+    int n_scales;
+};
+__global__ void __launch_bounds__(128) upsample_y_blocked_kernel(const __grid_constant__ UpYBlocked p, int CT, int H,
+                                                                 int W, float* __restrict__ out) {
+    const int x = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    const int yb = blockIdx.y;
+    const int c = blockIdx.z * blockDim.y + threadIdx.y;
+    if (x >= W || c >= CT) return;
+    float4 acc[kTY];
+#pragma unroll
+    for (int i = 0; i < kTY; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < p.n_scales; ++s) {
+        const int f0 = p.first[s][yb], R = p.rows[s][yb], rs = p.rs[s];
+        const float* t = p.tmp[s] + ((size_t)c * p.ho[s] + f0) * W + x;
+        const float4* wt = (const float4*)(p.w[s] + (size_t)yb * rs * kTY);
+        for (int r = 0; r < R; ++r) {
+            const float4 v = *(const float4*)(t + (size_t)r * W);
+#pragma unroll
+            for (int q = 0; q < kTY / 4; ++q) {
+                const float4 w4 = __ldg(wt + r * (kTY / 4) + q);
+                const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float4& a = acc[q * 4 + j];
+                    a.x = fmaf(ws[j], v.x, a.x);
+                    a.y = fmaf(ws[j], v.y, a.y);
+                    a.z = fmaf(ws[j], v.z, a.z);
+                    a.w = fmaf(ws[j], v.w, a.w);
+                }
+            }
+        }
+    }
+    float* o = out + ((size_t)c * H + (size_t)yb * kTY) * W + x;
+#pragma unroll
+    for (int i = 0; i < kTY; ++i)
+        if (yb * kTY + i < H) *(float4*)(o + (size_t)i * W) = acc[i];
+}
+
 }  // namespace
 
 void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t* out, int h, int w, int hp, int wp,
@@ -169,7 +228,8 @@ void upsample_avg_launch2(const UpsampleScale* scales, int n_scales, int n_img, 
         const UpsampleScale& u = scales[s];
         float* tmp = scratch + off;
         off += (size_t)CT * u.ho * W;
-        dim3 grid(cdiv(W, 128), u.ho, CT);
+        OPB_REQUIRE(u.cstride % 4 == 0 && u.cstride >= ((C + 3) / 4) * 4, "upsample: source channel stride must cover C rounded up to 4");
+        dim3 grid(cdiv(W, 128), u.ho, n_img * ((C + 3) / 4));
         upsample_x_kernel<<<grid, 128, 0, stream>>>(u.src, u.ho, u.wo, u.cstride, C, W, u.x_first, u.x_w, tmp);
         OPB_CUDA(cudaGetLastError());
         p.tmp[s] = tmp;
@@ -177,7 +237,22 @@ void upsample_avg_launch2(const UpsampleScale* scales, int n_scales, int n_img, 
         p.yw[s] = u.y_w;
         p.ho[s] = u.ho;
     }
-    if (W % 4 == 0) {
+    if (W % 4 == 0 && scales[0].yb_w != nullptr) {
+        UpYBlocked b;
+        memset(&b, 0, sizeof(b));
+        b.n_scales = n_scales;
+        for (int s = 0; s < n_scales; ++s) {
+            b.tmp[s] = p.tmp[s];
+            b.first[s] = scales[s].yb_first;
+            b.rows[s] = scales[s].yb_rows;
+            b.w[s] = scales[s].yb_w;
+            b.ho[s] = scales[s].ho;
+            b.rs[s] = scales[s].yb_rs;
+        }
+        dim3 block(64, 2);
+        dim3 grid(cdiv(W / 4, 64), cdiv(H, kTY), cdiv(CT, 2));
+        upsample_y_blocked_kernel<<<grid, block, 0, stream>>>(b, CT, H, W, out_planar);
+    } else if (W % 4 == 0) {
         dim3 grid(cdiv(W / 4, 64), H, CT);
         upsample_y_kernel<4><<<grid, 64, 0, stream>>>(p, CT, H, W, out_planar);
     } else {
