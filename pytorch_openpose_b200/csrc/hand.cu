@@ -7,9 +7,8 @@
 //
 //   hand_smooth_kernel   same exact-float64 separable filter as peaks.cu; writes label[i] = i for mask pixels,
 //                        -1 elsewhere
-//   hand_merge_kernel    union-find over the W / NW / N / NE neighbours (atomicMin hooking); roots are the
-//                        smallest linear index of a component == raster order of first pixels
-//   hand_flatten_kernel  path compression + per-root float64 sums of raw values (atomicAdd)
+//   hand_runs / merge / compress / flatten   run-based union-find (atomicMin hooking); roots are the smallest linear
+//                        index of a component == raster order of first pixels; per-root float64 sums of raw values
 //   hand_select_kernel   one CTA per map: argmax over roots (sum desc, root asc), then argmax over pixels of
 //                        (label == best ? raw : 0) (value desc, index asc)
 // The component sums are accumulated in a different order than numpy's pairwise np.sum, so the choice of
@@ -107,36 +106,100 @@ __device__ void uf_union(int* L, int a, int b) {
     }
 }
 
+// ---- connected components, 8-connectivity -------------------------------------------------------------------------
+// Labels are built run-first so that even one giant component (a map that is above the threshold everywhere) stays
+// cheap: (1) every mask pixel points at the first pixel of its horizontal run, (2) runs of adjacent rows are united
+// once per touching pair (union-find over run heads only, atomicMin hooking: the root is the smallest raster index
+// of the component), (3) run heads are compressed to their root, (4) every pixel resolves label[label[i]].
+
+// (1) one warp per image row
+__global__ void hand_runs_kernel(int* __restrict__ labels, int h, int w) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= h) return;
+    int* L = labels + ((size_t)blockIdx.y * h + row) * w;
+    int carry = -1;                                     // head of the run that reaches the start of this segment
+    for (int x0 = 0; x0 < w; x0 += 32) {
+        const int x = x0 + lane;
+        const bool on = x < w && L[x] >= 0;
+        const unsigned bits = __ballot_sync(0xffffffffu, on);
+        // closest zero bit strictly below this lane
+        const unsigned below = ~bits & ((1u << lane) - 1);
+        int head;
+        if (below) head = x0 + (32 - __clz(below));     // run starts right after the highest zero below
+        else head = carry >= 0 ? carry : x0;            // run reaches the segment start
+        if (on) L[x] = row * w + head;
+        // carry for the next segment: head of the run containing lane 31, if any
+        const int head31 = __shfl_sync(0xffffffffu, head, 31);
+        carry = (bits >> 31) ? head31 : -1;
+    }
+}
+
+// (2) unite every run with the runs of the row above that touch it (columns xs-1 .. xe+1)
 __global__ void hand_merge_kernel(int* __restrict__ labels, int h, int w) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= w || y == 0) return;
+    int* L = labels + (size_t)blockIdx.z * h * w;
+    const int i = y * w + x;
+    const int mine = L[i];
+    if (mine < 0) return;
+    const int* up = L + i - w;
+    const bool u0 = up[0] >= 0;
+    // an upper run that STARTS at x+1 touches this run
+    if (x + 1 < w && up[1] >= 0 && !u0) uf_union(L, mine, up[1]);
+    // at the head of this run (decided by geometry: the head's own entry may already have been hooked by another
+    // thread): the upper run covering x-1 or x
+    if (x == 0 || L[i - 1] < 0) {
+        if (x > 0 && up[-1] >= 0) uf_union(L, mine, up[-1]);
+        else if (u0) uf_union(L, mine, up[0]);
+    }
+}
+
+// (3) compress run heads to their roots
+__global__ void hand_compress_kernel(int* __restrict__ labels, int h, int w) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     if (x >= w) return;
     int* L = labels + (size_t)blockIdx.z * h * w;
     const int i = y * w + x;
     if (L[i] < 0) return;
-    if (x > 0 && L[i - 1] >= 0) uf_union(L, i, i - 1);
-    if (y > 0) {
-        if (L[i - w] >= 0) uf_union(L, i, i - w);
-        if (x > 0 && L[i - w - 1] >= 0) uf_union(L, i, i - w - 1);
-        if (x + 1 < w && L[i - w + 1] >= 0) uf_union(L, i, i - w + 1);
-    }
+    const bool head = x == 0 || L[i - 1] < 0;
+    if (!head) return;
+    const int root = uf_find(L, i);
+    if (root != i) L[i] = root;                        // only ever lowers an entry towards its root
 }
 
+// (4) resolve every pixel and accumulate the raw-map sum of its component
 __global__ void hand_flatten_kernel(const float* __restrict__ heat, int chan_stride_maps, int* __restrict__ labels,
                                     double* __restrict__ sums, int h, int w) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= w) return;
     const int m = blockIdx.z;
     const int crop = m / 21, part = m - crop * 21;
     int* L = labels + (size_t)m * h * w;
     const int i = y * w + x;
-    if (L[i] < 0) return;
-    const int root = uf_find(L, i);
-    // every thread only ever lowers its own entry to its root: concurrent finds stay valid
-    if (root != i) L[i] = root;
-    const float v = heat[((size_t)crop * chan_stride_maps + part) * h * w + i];
-    atomicAdd(&sums[(size_t)m * h * w + root], (double)v);
+    int root = -1;
+    double v = 0.0;
+    if (x < w && L[i] >= 0) {
+        root = __ldcg(L + __ldcg(L + i));              // pixel -> run head -> root
+        // a run head may itself still point one hop short if it was hooked after its own compression pass started
+        root = uf_find(L, root);
+        L[i] = root;
+        v = (double)heat[((size_t)crop * chan_stride_maps + part) * h * w + i];
+    }
+    // warp-aggregated atomics: lanes of a warp almost always share one root
+    const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
+    if (root < 0) return;
+    const unsigned same = __match_any_sync(active, root);
+    if (active == 0xffffffffu && same == active) {
+        double tot = v;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sums[(size_t)m * h * w + root], tot);
+    } else {
+        atomicAdd(&sums[(size_t)m * h * w + root], v);
+    }
 }
 
 struct Best {
@@ -209,7 +272,12 @@ void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_m
                                                hb.labels, smoothed_out);
     OPB_CUDA(cudaGetLastError());
     dim3 g2(cdiv(w, 128), h, maps);
+    dim3 g0(cdiv(h, 4), maps);
+    hand_runs_kernel<<<g0, 128, 0, stream>>>(hb.labels, h, w);
+    OPB_CUDA(cudaGetLastError());
     hand_merge_kernel<<<g2, 128, 0, stream>>>(hb.labels, h, w);
+    OPB_CUDA(cudaGetLastError());
+    hand_compress_kernel<<<g2, 128, 0, stream>>>(hb.labels, h, w);
     OPB_CUDA(cudaGetLastError());
     hand_flatten_kernel<<<g2, 128, 0, stream>>>(heat_planar, chan_stride_maps, hb.labels, hb.sums, h, w);
     OPB_CUDA(cudaGetLastError());

@@ -123,3 +123,18 @@ def test_hand_peaks_rectangular_and_empty():
     got = G.hand_peaks(hm.transpose(2, 0, 1))
     assert np.array_equal(got, O.hand_postprocess(hm))
     assert np.array_equal(G.hand_peaks(np.zeros((22, 30, 30), np.float32)), np.zeros((21, 3)))
+
+
+def test_hand_peaks_giant_and_many_components():
+    """One component covering the whole map (run-based union-find worst case) and a map with hundreds of
+    small components: identical to the oracle."""
+    from tests import gpu_util as G
+    rng = np.random.default_rng(12)
+    hm = np.zeros((120, 150, 22))
+    hm[:, :, :11] = 0.05 + smooth_noise_maps(120, 150, 11, 3, 0.002, 40)           # everywhere above 0.03
+    hm[:, :, 11:] = smooth_noise_maps(120, 150, 11, 1.0, 0.06, 41)                  # speckle: many components
+    hm = hm.astype(np.float32).astype(np.float64)
+    got = G.hand_peaks(hm.transpose(2, 0, 1))
+    ref = O.hand_postprocess(hm)
+    assert np.array_equal(got, ref)
+    assert (ref[:, 2] > 0).sum() >= 15
