@@ -6,6 +6,8 @@
 //   * conv_direct  : scalar reference convolution with the tensor-core kernel's exact I/O contract; only
 //                    the cross-check entry point opb_conv2d(impl=1) reaches it.
 #include "opb_common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 namespace opb {
 namespace {
@@ -85,6 +87,172 @@ __global__ void __launch_bounds__(128) conv_first_kernel(const uint8_t* __restri
     }
 }
 
+// ---- conv1_1 on the legacy tensor-core path (mma.sync m16n8k16, bf16 x bf16 -> fp32) -----------------------------
+// K = 27 (3x3 taps x 3 channels) is far too thin for a tcgen05 tile pipeline, but as a register-fragment GEMM it
+// turns the layer from FMA-issue bound (0.25 ms/frame on CUDA cores) into an output-bandwidth bound one.
+// One CTA (4 warps) = 128 consecutive pixels of one image row; warp = 32 pixels x 64 channels x K 32 (27 + 5 zero).
+// The input halo (3 rows x 130 pixels, bytes; 128 outside the image, which normalises to exactly 0) sits in shared
+// memory; A fragments are built from it on the fly (x/256 - 0.5 is exact in bf16), B fragments (weights) live in
+// registers for the whole grid-stride loop; the 128 x 64 bf16 tile is staged in swizzled shared memory and written
+// as one contiguous 16 KB run.
+__device__ __forceinline__ uint32_t pack_norm(uint8_t lo, uint8_t hi) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn((float)lo * (1.0f / 256.0f) - 0.5f, (float)hi * (1.0f / 256.0f) - 0.5f);
+    return *(const uint32_t*)&h;
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kSegPx = 128;                       // pixels per CTA iteration
+constexpr int kRowBytes = (kSegPx + 2) * 3;       // 390 bytes per staged input row
+
+__global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                                                             const float* __restrict__ w /*[27][64]*/,
+                                                             const float* __restrict__ bias, int N, int H, int W,
+                                                             int out_cstride, int segs_per_row, int total_segs) {
+    __shared__ uint8_t srow[3][kRowBytes + 2];
+    __shared__ uint4 stile[kSegPx * 8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int g = lane >> 2, t = lane & 3;
+
+    // per-lane k offsets inside the staged halo: k -> (dy, dx, c); k >= 27 reads a dedicated pad byte (value 128)
+    int koff[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const int k = ks * 16 + t * 2 + (q & 1) + (q >> 1) * 8;
+            const int tap = k / 3, c = k - tap * 3;
+            koff[ks][q] = k < 27 ? (tap / 3) * (kRowBytes + 2) + (tap % 3) * 3 + c : -1;
+        }
+    // B fragments: b[j][ks][0] = (W[kb+2t][n], W[kb+2t+1][n]), b[j][ks][1] = (W[kb+2t+8][n], W[kb+2t+9][n]), n = 8j+g
+    uint32_t bfrag[8][2][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+                const int k0 = ks * 16 + t * 2 + hh * 8, n = j * 8 + g;
+                const float w0 = k0 < 27 ? w[k0 * 64 + n] : 0.f;
+                const float w1 = k0 + 1 < 27 ? w[(k0 + 1) * 64 + n] : 0.f;
+                const __nv_bfloat162 h2 = __floats2bfloat162_rn(w0, w1);
+                bfrag[j][ks][hh] = *(const uint32_t*)&h2;
+            }
+    float bias_r[8][2];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        bias_r[j][0] = bias[j * 8 + t * 2];
+        bias_r[j][1] = bias[j * 8 + t * 2 + 1];
+    }
+    const uint8_t* flat = &srow[0][0];
+
+    // halo bytes of a segment, fetched into registers one iteration ahead so that the global-load latency overlaps
+    // the MMAs and stores of the current segment
+    constexpr int kPre = (3 * kRowBytes + 127) / 128;          // 10 bytes per thread
+    uint8_t pre[kPre];
+    auto fetch = [&](int seg) {
+        const int sx = seg % segs_per_row;
+        const int y = (seg / segs_per_row) % H;
+        const size_t img = seg / (segs_per_row * H);
+        const int x0 = sx * kSegPx;
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+            const int i = threadIdx.x + q * 128;
+            const int r = i / kRowBytes, e = i - r * kRowBytes;
+            const int px = e / 3, c = e - px * 3;
+            const int yy = y + r - 1, xx = x0 + px - 1;
+            uint8_t v = 128;                                   // 128/256 - 0.5 == 0: zero padding
+            if (i < 3 * kRowBytes && yy >= 0 && yy < H && xx >= 0 && xx < W)
+                v = __ldg(in + ((img * H + yy) * (size_t)W + xx) * 3 + c);
+            pre[q] = v;
+        }
+    };
+    if ((int)blockIdx.x < total_segs) fetch(blockIdx.x);
+
+    for (int seg = blockIdx.x; seg < total_segs; seg += gridDim.x) {
+        const int sx = seg % segs_per_row;
+        const int y = (seg / segs_per_row) % H;
+        const size_t img = seg / (segs_per_row * H);
+        const int x0 = sx * kSegPx;
+        const int npx = min(kSegPx, W - x0);
+        __syncthreads();                                   // previous iteration finished with srow / stile
+#pragma unroll
+        for (int q = 0; q < kPre; ++q) {
+            const int i = threadIdx.x + q * 128;
+            if (i < 3 * kRowBytes) srow[i / kRowBytes][i % kRowBytes] = pre[q];
+        }
+        __syncthreads();
+        if (seg + (int)gridDim.x < total_segs) fetch(seg + gridDim.x);
+        // A fragments of both 16-pixel tiles and both k steps (16 registers), then two passes over the 64 output
+        // channels (32 accumulators live at a time keeps the kernel at 5 CTAs per SM)
+        uint32_t afrag[2][2][4];
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+            const int p0 = (warp * 32 + mt * 16 + g) * 3;          // byte offset of pixel row g in the halo row
+            const int p1 = p0 + 8 * 3;                             // row g + 8
+#pragma unroll
+            for (int ks = 0; ks < 2; ++ks) {
+                // a0: (row g, k pair 0), a1: (row g+8, pair 0), a2: (row g, pair +8), a3: (row g+8, pair +8)
+                const int o0 = koff[ks][0], o1 = koff[ks][1], o2 = koff[ks][2], o3 = koff[ks][3];
+                afrag[mt][ks][0] = pack_norm(o0 >= 0 ? flat[p0 + o0] : 128, o1 >= 0 ? flat[p0 + o1] : 128);
+                afrag[mt][ks][1] = pack_norm(o0 >= 0 ? flat[p1 + o0] : 128, o1 >= 0 ? flat[p1 + o1] : 128);
+                afrag[mt][ks][2] = pack_norm(o2 >= 0 ? flat[p0 + o2] : 128, o3 >= 0 ? flat[p0 + o3] : 128);
+                afrag[mt][ks][3] = pack_norm(o2 >= 0 ? flat[p1 + o2] : 128, o3 >= 0 ? flat[p1 + o3] : 128);
+            }
+        }
+        uint32_t* st32 = (uint32_t*)stile;
+#pragma unroll
+        for (int jh = 0; jh < 2; ++jh) {
+            float acc[2][4][4];
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    acc[mt][jj][0] = acc[mt][jj][2] = bias_r[jh * 4 + jj][0];
+                    acc[mt][jj][1] = acc[mt][jj][3] = bias_r[jh * 4 + jj][1];
+                }
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj)
+                        mma_bf16_16816(acc[mt][jj], afrag[mt][ks], bfrag[jh * 4 + jj][ks][0], bfrag[jh * 4 + jj][ks][1]);
+            // ReLU -> bf16 pairs -> swizzled staging tile: pixel p, channels (8j + 2t, +1) live in chunk j at word t
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+                for (int hr = 0; hr < 2; ++hr) {
+                    const int p = warp * 32 + mt * 16 + g + hr * 8;
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int j = jh * 4 + jj;
+                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(acc[mt][jj][hr * 2], 0.f), fmaxf(acc[mt][jj][hr * 2 + 1], 0.f));
+                        st32[(p * 8 + (j ^ (p & 7))) * 4 + t] = *(const uint32_t*)&h2;
+                    }
+                }
+        }
+        __syncthreads();
+        const size_t pix0 = (img * H + y) * (size_t)W + x0;
+        if (out_cstride == 64) {
+            uint4* o = (uint4*)(out + pix0 * 64);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int q = i * 128 + threadIdx.x;               // pixel = q / 8, chunk = q % 8
+                if ((q >> 3) < npx) o[q] = stile[(q & ~7) + ((q & 7) ^ ((q >> 3) & 7))];
+            }
+        } else if ((int)threadIdx.x < npx) {
+            uint4* o = (uint4*)(out + (pix0 + threadIdx.x) * out_cstride);
+#pragma unroll
+            for (int c8 = 0; c8 < 8; ++c8) o[c8] = stile[threadIdx.x * 8 + (c8 ^ (threadIdx.x & 7))];
+        }
+    }
+}
+
 // ---- 2x2 max-pool, 8 channels (16 bytes) per thread -------------------------------------------------
 __device__ __forceinline__ uint4 bf16x8_max(uint4 a, uint4 b) {
     uint4 r;
@@ -160,9 +328,19 @@ void conv_first_launch(const TensorView& in_u8, const TensorView& out, const flo
     OPB_REQUIRE(in_u8.elem == 1 && in_u8.c == 3 && in_u8.cstride == 3, "conv_first: input must be dense u8 HWC3");
     OPB_REQUIRE(out.elem == 2 && out.c == 64 && out.cstride % 8 == 0 && out.coff == 0, "conv_first: output bf16 64ch");
     OPB_REQUIRE(in_u8.w % 4 == 0, "conv_first: padded width must be a multiple of 4");
-    const size_t total = in_u8.pixels() / 4;                   // one thread per 4-pixel strip
-    conv_first_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(
-        (const uint8_t*)in_u8.base, (__nv_bfloat16*)out.base, w27x64, bias, in_u8.n, in_u8.h, in_u8.w, out.cstride);
+    static const bool use_simt = getenv("OPB_CONV1_SIMT") != nullptr;      // CUDA-core variant kept for cross-checks
+    if (use_simt) {
+        const size_t total = in_u8.pixels() / 4;               // one thread per 4-pixel strip
+        conv_first_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(
+            (const uint8_t*)in_u8.base, (__nv_bfloat16*)out.base, w27x64, bias, in_u8.n, in_u8.h, in_u8.w, out.cstride);
+    } else {
+        const int segs_per_row = cdiv(in_u8.w, kSegPx);
+        const long long total_segs = (long long)segs_per_row * in_u8.h * in_u8.n;
+        OPB_REQUIRE(total_segs < (1ll << 31), "conv_first: too many pixels");
+        const int grid = (int)std::min<long long>(total_segs, 148 * 16);
+        conv_first_mma_kernel<<<grid, 128, 0, stream>>>((const uint8_t*)in_u8.base, (__nv_bfloat16*)out.base, w27x64, bias,
+                                                       in_u8.n, in_u8.h, in_u8.w, out.cstride, segs_per_row, (int)total_segs);
+    }
     OPB_CUDA(cudaGetLastError());
 }
 

@@ -90,3 +90,43 @@ def test_hand_batch_equals_single():
     batch = hand(crops)
     for i in range(3):
         assert np.array_equal(batch[i], hand(crops[i]))
+
+
+@pytest.mark.parametrize("shape,scales", [((97, 131, 3), (0.5, 1.0)), ((61, 40, 3), (1.0,)), ((33, 200, 3), (0.5, 2.0))])
+def test_body_odd_sizes(shape, scales):
+    """Ragged frames: widths not divisible by 4/8, maps smaller than a tile, very wide / very tall aspect ratios."""
+    from pytorch_openpose_b200 import Body
+    sd = O.make_weights("body", 3)
+    img = np.random.default_rng(7).integers(0, 256, shape, dtype=np.uint8)
+    body = Body(sd, scale_search=list(scales))
+    cand, subset = body(img)
+    heat, paf = body.last_maps(img.shape)
+    rc, rs = O.body_postprocess(heat.astype(np.float64), paf.astype(np.float64), shape[0])
+    assert cand.shape == rc.shape and np.array_equal(cand, rc) and np.array_equal(subset, rs)
+    _, _, rheat, rpaf = O.body_call(img, sd, scales, use_cv2=True, return_maps=True)
+    assert _rel(heat, rheat) <= 1e-2 and _rel(paf, rpaf) <= 1e-2
+
+
+def test_hand_rectangular_crop():
+    from pytorch_openpose_b200 import Hand
+    sd = O.make_weights("hand", 5, "kaiming")
+    hand = Hand(sd, scale_search=[0.5, 1.0])
+    import cv2
+    crop = cv2.GaussianBlur(np.random.default_rng(4).integers(0, 256, (50, 37, 3), dtype=np.uint8), (0, 0), 2)
+    peaks = hand(crop)
+    maps = hand.last_maps(crop.shape)[0]
+    assert np.array_equal(peaks, O.hand_postprocess(maps.astype(np.float64)))
+    _, ravg = O.hand_call(crop, sd, (0.5, 1.0), return_maps=True)
+    assert _rel(maps, ravg) <= 2e-2          # Kaiming weights: bf16 through ~50 layers (DESIGN.md section 2)
+
+
+def test_synthetic_scene_through_public_api_grouping(golden):
+    """The crowded-scene config (BASELINE config 5): 50 people injected at the map boundary -> identical result."""
+    from tests import gpu_util as G
+    g = golden("body_postproc")
+    heat, paf, _ = O.synthetic_scene(720, 1280, (10, 5), seed=0)
+    cand, pb, cand_dev = G.find_peaks(heat.transpose(2, 0, 1))
+    subset, conns, cc = G.group_limbs(paf.transpose(2, 0, 1), cand_dev, pb)
+    assert len(cand) == 900 and np.array_equal(cand, g["cand_p50"]) and np.array_equal(subset, g["subset_p50"])
+    total_pairs = sum((pb[a] - pb[a - 1]) * (pb[b] - pb[b - 1]) for a, b in O.LIMB_SEQ)
+    assert total_pairs == 47500
