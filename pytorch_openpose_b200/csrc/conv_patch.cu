@@ -56,9 +56,9 @@ template <int BLOCK_N, int MODE>
 struct PCfg {
     static constexpr int kPitch = MODE == 0 ? 24 : 16;                 // patch columns (rows of 128 B per patch line)
     static constexpr int kPatchBytesMax = kPitch * (kTile + 6) * 128;  // ks = 7
-    static constexpr int kNumPatch = MODE == 0 ? 2 : 3;
+    static constexpr int kNumPatch = 2;
     static constexpr int kBBytes = BLOCK_N * 128;
-    static constexpr int kBStages = BLOCK_N == 128 ? 5 : 8;
+    static constexpr int kBStages = MODE == 0 ? (BLOCK_N == 128 ? 5 : 8) : (BLOCK_N == 128 ? 8 : 12);
     static constexpr int kTmemCols = kAccStages * kHalves * BLOCK_N;   // 512 / 256
     static constexpr int kNumBars = 2 * kNumPatch + 2 * kBStages + 2 * kAccStages;
     static constexpr int kBarBytes = kNumBars * 8 + 16;
