@@ -144,7 +144,7 @@ int opb_smooth_debug(opb_context* ctx, const float* dev_heat, int parts, int hei
 
 /* Debug/cross-check: generic convolution on NHWC bf16 device tensors through either the tcgen05
  * implicit-GEMM path the networks use (impl = 0), the scalar reference kernel (impl = 1), or a specific
- * tensor-core variant (2 = per-tap tiles, 3 / 4 = patch-resident MODE 0 / 1).  weight is host OIHW fp32.
+ * tensor-core variant (2 = per-tap tiles, 3 / 4 = patch-resident MODE 0 / 1, 5 = CTA pair).  weight is host OIHW fp32.
  * out_fp32 != 0 writes fp32.  pool != 0 fuses a 2x2/2 max-pool (impl 0 only).                         */
 int opb_conv2d(opb_context* ctx, const void* dev_in_bf16, int n, int h, int w, int cin, const float* weight,
                const float* bias, int cout, int k, int relu, int pool, int out_fp32, void* dev_out, int impl);

@@ -807,16 +807,18 @@ int opb_conv2d(opb_context* ctx, const void* dev_in, int n, int h, int w, int ci
         op.w = dp.upload(wd);
         op.bias = dp.upload(bd);
         op.cout_pad = cout_pad; op.cout_store = cout_store; op.ks = k; op.relu = relu != 0; op.pool = pool != 0;
-        // impl: 0 = the path the networks use, 1 = scalar cross-check, 2 = per-tap tiles, 3 / 4 = patch MODE 0 / 1
+        // impl: 0 = the path the networks use, 1 = scalar cross-check, 2 = per-tap tiles, 3 / 4 = patch MODE 0 / 1,
+        // 5 = CTA-pair (cta_group::2) kernel
         int sel = impl;
         if (impl == 0) sel = (k > 1 && default_conv_impl() >= 0) ? 3 + default_conv_impl() : 2;
-        if ((sel == 3 || sel == 4) && k == 1) sel = 2;
+        if ((sel == 3 || sel == 4 || sel == 5) && k == 1) sel = 2;
         if (sel == 1) {
             conv_direct_launch(op, ctx->stream);
         } else if (sel == 2) {
             conv_tc_launch({op}, bn, ctx->stream, ctx->num_sms);
         } else {
-            std::unique_ptr<ConvLaunch> L(conv_patch_plan({op}, bn, ctx->num_sms, sel - 3));
+            std::unique_ptr<ConvLaunch> L(sel == 5 ? conv_pair_plan({op}, bn, ctx->num_sms)
+                                                   : conv_patch_plan({op}, bn, ctx->num_sms, sel - 3));
             L->run(ctx->stream);
         }
         ctx->launches += 1;

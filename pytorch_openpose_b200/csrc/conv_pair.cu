@@ -1,0 +1,413 @@
+// CTA-pair (tcgen05 cta_group::2) variant of the patch-resident convolution (conv_patch.cu, MODE 1).
+//
+// Why: with cta_group::1 every 128x128x16 UMMA reads 4 KB of A and 4 KB of B from shared memory in 64 cycles
+// (128 B/clk) while TMA keeps writing ~45 B/clk into the same shared memory; ncu shows the tensor pipe 82 % busy.
+// A CTA pair issues ONE UMMA with M = 256: each SM contributes its own 128 A rows (its own halo patch, its own
+// TMEM accumulator) and only HALF of the weight tile (N/2 rows), so per SM the operand reads drop to 6 KB per 64
+// cycles and the weight traffic L2->SM halves.
+//
+//   cluster (2,1,1): CTA rank r owns super-tile 2*pair + r of a problem (same weights, same n tile).
+//   leader (rank 0) : arms the full barriers for the bytes of BOTH CTAs, issues every tcgen05.mma.cta_group::2 and
+//                     commits with .multicast::cluster so the empty / accumulator-full barriers of both CTAs fire.
+//   both CTAs       : TMA producers (patches + their half of the weights; complete_tx goes to the leader's barrier),
+//                     epilogue (own TMEM rows), which releases the accumulator by arriving on the LEADER's barrier.
+#include "opb_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace opb {
+namespace {
+
+using namespace tc;
+
+constexpr int kThreads = 224;
+constexpr int kAccStages = 2;
+constexpr int kHalves = 2;
+constexpr int kTile = 16;
+constexpr int kPitch = 16;
+constexpr int FLAG_RELU = 1, FLAG_F32 = 2, FLAG_POOL = 4;
+
+struct QProb {
+    void* out;
+    const float* bias;
+    int H, W, N;
+    int tiles_x, tiles_y;
+    int m_tiles, m_pairs;        // super-tiles of the problem, and pairs of them (rounded up)
+    int out_cstride, cout_store;
+    int n_tiles_n, cin_chunks;
+    int pair_begin, flags;
+};
+
+struct alignas(64) PairParams {
+    CUtensorMap tmA[kConvMaxProblems];
+    CUtensorMap tmW[kConvMaxProblems];
+    QProb prob[kConvMaxProblems];
+    int nprob, total_pairs, ks;
+};
+static_assert(sizeof(PairParams) <= 4000, "kernel parameter space");
+
+template <int BLOCK_N>
+struct QCfg {
+    static constexpr int kPatchBytesMax = kPitch * (kTile + 6) * 128;      // 45056 (ks = 7)
+    static constexpr int kNumPatch = 3;
+    static constexpr int kBHalfBytes = (BLOCK_N / 2) * 128;                 // this CTA's half of a weight stage
+    static constexpr int kBStages = 8;
+    static constexpr int kTmemCols = kAccStages * kHalves * BLOCK_N;
+    static constexpr int kNumBars = 2 * kNumPatch + 2 * kBStages + 2 * kAccStages;
+    static constexpr int kBarBytes = kNumBars * 8 + 16;
+    static constexpr int kBiasBytes = kAccStages * BLOCK_N * 4;
+    static constexpr int kSmemBytes = 1024 + kNumPatch * kPatchBytesMax + kBStages * kBHalfBytes + kBarBytes + kBiasBytes;
+    static_assert(kBHalfBytes % 1024 == 0, "swizzle atoms must stay 1024-B aligned");
+    static_assert(kSmemBytes <= 232448, "shared memory budget");
+};
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+struct TileCoord {
+    int pi, img, x0, y0, n0;
+    bool real;                   // false: padding tile of an odd problem (computed, never stored)
+};
+__device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, int rank, int block_n) {
+    int pi = 0;
+    while (pi + 1 < p.nprob && pr >= p.prob[pi + 1].pair_begin) ++pi;
+    const QProb& q = p.prob[pi];
+    const int local = pr - q.pair_begin;
+    const int nt = local % q.n_tiles_n;
+    const int mp = local / q.n_tiles_n;
+    int mt = 2 * mp + rank;
+    TileCoord c;
+    c.real = mt < q.m_tiles;
+    if (!c.real) mt = q.m_tiles - 1;
+    const int per_img = q.tiles_x * q.tiles_y;
+    const int img = mt / per_img;
+    const int r = mt - img * per_img;
+    const int tyi = r / q.tiles_x;
+    const int txi = r - tyi * q.tiles_x;
+    c.pi = pi;
+    c.img = img;
+    c.x0 = txi * kTile;
+    c.y0 = tyi * kTile;
+    c.n0 = nt * block_n;
+    return c;
+}
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_pair_kernel(const __grid_constant__ PairParams p) {
+    using C = QCfg<BLOCK_N>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* patches = smem;
+    uint8_t* bstages = smem + C::kNumPatch * C::kPatchBytesMax;
+    uint64_t* pfull = (uint64_t*)(bstages + C::kBStages * C::kBHalfBytes);
+    uint64_t* pempty = pfull + C::kNumPatch;
+    uint64_t* bfull = pempty + C::kNumPatch;
+    uint64_t* bempty = bfull + C::kBStages;
+    uint64_t* tfull = bempty + C::kBStages;
+    uint64_t* tempty = tfull + kAccStages;
+    uint32_t* tmem_slot = (uint32_t*)(tempty + kAccStages);
+    float* sbias = (float*)((uint8_t*)pfull + C::kBarBytes);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+    const int rank = (int)cluster_ctarank();            // 0 = leader
+    const int cluster_id = blockIdx.x >> 1;
+    const int n_clusters = gridDim.x >> 1;
+    const int ks = p.ks;
+    const int pad = ks >> 1;
+    const int patch_rows = kTile + ks - 1;
+    const uint32_t patch_bytes = (uint32_t)(kPitch * patch_rows * 128);
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < p.nprob; ++i) {
+            prefetch_tensormap(&p.tmA[i]);
+            prefetch_tensormap(&p.tmW[i]);
+        }
+        for (int s = 0; s < C::kNumPatch; ++s) {
+            mbar_init(&pfull[s], 1);
+            mbar_init(&pempty[s], 1);
+        }
+        for (int s = 0; s < C::kBStages; ++s) {
+            mbar_init(&bfull[s], 1);
+            mbar_init(&bempty[s], 1);
+        }
+        for (int a = 0; a < kAccStages; ++a) {
+            mbar_init(&tfull[a], 1);
+            mbar_init(&tempty[a], 256);                 // 128 epilogue threads of each CTA (leader's copy is used)
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm(tmem_slot, C::kTmemCols);
+    tc_fence_before();
+    cluster_sync_all();                                 // barrier inits + TMEM allocation visible in both CTAs
+    tc_fence_after();
+    const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+    if (warp == 6) {
+        // ================= patch (A) producer: own tile =================
+        int pb = 0;
+        uint32_t pphase = 0;
+        for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
+            const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
+            const int cin_chunks = p.prob[tc.pi].cin_chunks;
+            const CUtensorMap* tmA = &p.tmA[tc.pi];
+            for (int cc = 0; cc < cin_chunks; ++cc) {
+                for (int dx = 0; dx < ks; ++dx) {
+                    mbar_wait(&pempty[pb], pphase ^ 1, 10);
+                    if (rank == 0) mbar_arrive_expect_tx_elect(&pfull[pb], 2 * patch_bytes);
+                    tma_load_4d_2sm_elect(patches + pb * C::kPatchBytesMax, tmA, &pfull[pb], cc * 64, tc.x0 - pad + dx,
+                                          tc.y0 - pad, tc.img);
+                    if (++pb == C::kNumPatch) { pb = 0; pphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 0) {
+        // ================= weight (B) producer: this CTA's half of the N rows =================
+        int bs = 0;
+        uint32_t bphase = 0;
+        for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
+            const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
+            const int cin_chunks = p.prob[tc.pi].cin_chunks;
+            const CUtensorMap* tmW = &p.tmW[tc.pi];
+            for (int cc = 0; cc < cin_chunks; ++cc) {
+                for (int i = 0; i < ks * ks; ++i) {
+                    const int tap = (i % ks) * ks + (i / ks);              // dx outer, dy inner (matches the MMA walk)
+                    mbar_wait(&bempty[bs], bphase ^ 1, 11);
+                    if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[bs], 2 * C::kBHalfBytes);
+                    tma_load_2d_2sm_elect(bstages + bs * C::kBHalfBytes, tmW, &bfull[bs], (tap * cin_chunks + cc) * 64,
+                                          tc.n0 + rank * (BLOCK_N / 2));
+                    if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (rank == 0) {
+            constexpr uint32_t idesc = make_idesc_2sm(BLOCK_N);
+            int pb = 0, bs = 0, acc = 0;
+            uint32_t pphase = 0, bphase = 0, acc_phase = 0;
+            for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
+                const TileCoord tc = decode_pair(p, pr, 0, BLOCK_N);
+                const QProb& q = p.prob[tc.pi];
+                uint32_t accum[kHalves] = {0, 0};
+                mbar_wait(&tempty[acc], acc_phase ^ 1, 12);               // both epilogues drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * (kHalves * BLOCK_N);
+                for (int cc = 0; cc < q.cin_chunks; ++cc) {
+                    for (int sh = 0; sh < ks; ++sh) {
+                        mbar_wait(&pfull[pb], pphase, 13);                // both CTAs' patches have landed
+                        tc_fence_after();
+                        const uint32_t patch_addr = smem_u32(patches + pb * C::kPatchBytesMax);
+                        for (int dy = 0; dy < ks; ++dy) {
+                            mbar_wait(&bfull[bs], bphase, 14);            // both weight halves have landed
+                            tc_fence_after();
+                            const uint64_t bdesc = make_desc(smem_u32(bstages + bs * C::kBHalfBytes), 1024);
+#pragma unroll
+                            for (int h = 0; h < kHalves; ++h) {
+                                const uint64_t adesc = make_desc(patch_addr + (uint32_t)((dy * kPitch + h * 8) * 128), kPitch * 128);
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    umma_bf16_2sm_elect(d_tmem + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, accum[h]);
+                                    accum[h] = 1;
+                                }
+                            }
+                            umma_commit_2sm_elect(&bempty[bs]);
+                            if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+                        }
+                        umma_commit_2sm_elect(&pempty[pb]);
+                        if (++pb == C::kNumPatch) { pb = 0; pphase ^= 1; }
+                    }
+                }
+                umma_commit_2sm_elect(&tfull[acc]);
+                if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else if (warp >= 2 && warp <= 5) {
+        // ================= epilogue: own 128 TMEM lanes per half =================
+        const int quad = warp & 3;
+        const int row = quad * 32 + lane;
+        const int ep_tid = threadIdx.x - 64;
+        const int tx = row & 7, ty = row >> 3;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
+            const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
+            const QProb& q = p.prob[tc.pi];
+            float* bias_s = sbias + acc * BLOCK_N;
+            if (ep_tid < BLOCK_N) bias_s[ep_tid] = __ldg(q.bias + tc.n0 + ep_tid);
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            const bool relu = q.flags & FLAG_RELU;
+            const bool pool = q.flags & FLAG_POOL;
+            const bool f32 = q.flags & FLAG_F32;
+            const int n_valid = q.cout_store - tc.n0;
+            const int y = tc.y0 + ty;
+
+            mbar_wait(&tfull[acc], acc_phase, 15);
+            tc_fence_after();
+#pragma unroll 1
+            for (int h = 0; h < kHalves; ++h) {
+                if (!tc.real || tc.x0 + 8 * h >= q.W) break;
+                const int x = tc.x0 + 8 * h + tx;
+                const bool inside = (x < q.W) && (y < q.H);
+                size_t pix;
+                bool writer;
+                if (pool) {
+                    pix = ((size_t)tc.img * (q.H >> 1) + (y >> 1)) * (q.W >> 1) + (x >> 1);
+                    writer = inside && !(tx & 1) && !(ty & 1);
+                } else {
+                    pix = ((size_t)tc.img * q.H + y) * q.W + x;
+                    writer = inside;
+                }
+                const size_t out_off = pix * q.out_cstride + tc.n0;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (kHalves * BLOCK_N) + h * BLOCK_N;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+                    if (c0 >= n_valid) break;
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c0, v);
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float a = __uint_as_float(v[j]) + bias_s[c0 + j];
+                        f[j] = relu ? fmaxf(a, 0.f) : a;
+                    }
+                    if (pool) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float m = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
+                            f[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                        }
+                    }
+                    if (writer) {
+                        if (f32) {
+                            float* o = (float*)q.out + out_off + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 4)
+                                if (c0 + j < n_valid) *(float4*)(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                        } else {
+                            __nv_bfloat16* o = (__nv_bfloat16*)q.out + out_off + c0;
+#pragma unroll
+                            for (int j = 0; j < 32; j += 8) {
+                                if (c0 + j < n_valid) {
+                                    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+                                    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+                                    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+                                    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+                                    uint4 u;
+                                    u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1; u.z = *(uint32_t*)&h2; u.w = *(uint32_t*)&h3;
+                                    *(uint4*)(o + j) = u;
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(&tempty[acc], 0);                         // release on the leader's barrier
+            if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    // the peer's shared memory and TMEM are operands of the leader's MMAs: nobody leaves before both are done
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, C::kTmemCols);
+    }
+}
+
+struct PairLaunch : ConvLaunch {
+    PairParams params;
+    int grid = 0, block_n = 128;
+    void run(cudaStream_t stream) const override;
+};
+
+template <int BN>
+void launch_pair(const PairLaunch& L, cudaStream_t stream) {
+    static bool attr = false;
+    if (!attr) {
+        OPB_CUDA(cudaFuncSetAttribute(conv_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, QCfg<BN>::kSmemBytes));
+        attr = true;
+    }
+    conv_pair_kernel<BN><<<L.grid, kThreads, QCfg<BN>::kSmemBytes, stream>>>(L.params);
+}
+
+void PairLaunch::run(cudaStream_t stream) const {
+    if (block_n == 128) launch_pair<128>(*this, stream);
+    else launch_pair<64>(*this, stream);
+    OPB_CUDA(cudaGetLastError());
+}
+
+}  // namespace
+
+ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms) {
+    OPB_REQUIRE(!ops.empty() && (int)ops.size() <= kConvMaxProblems, "conv_pair: 1..8 problems per launch");
+    OPB_REQUIRE(block_n == 64 || block_n == 128, "conv_pair: block_n must be 64 or 128");
+    auto L = std::make_unique<PairLaunch>();
+    PairParams& P = L->params;
+    memset(&P, 0, sizeof(P));
+    P.nprob = (int)ops.size();
+    P.ks = ops[0].ks;
+    OPB_REQUIRE(P.ks == 3 || P.ks == 7, "conv_pair: kernel size 3 or 7");
+    int pairs = 0;
+    for (int i = 0; i < P.nprob; ++i) {
+        const ConvOp& op = ops[i];
+        OPB_REQUIRE(op.ks == P.ks, "conv_pair: grouped problems must share the kernel size");
+        OPB_REQUIRE(op.in.elem == 2 && op.in.c % 64 == 0, "conv_pair: input must be bf16 with C % 64 == 0");
+        OPB_REQUIRE(op.in.cstride % 8 == 0 && op.in.coff % 8 == 0, "conv_pair: input slice must be 16-byte aligned");
+        OPB_REQUIRE(op.cout_pad % block_n == 0 && op.cout_store % 8 == 0 && op.cout_store <= op.cout_pad,
+                    "conv_pair: bad output channel padding");
+        OPB_REQUIRE(op.out.elem == 2 || op.out.elem == 4, "conv_pair: output must be bf16 or fp32");
+        OPB_REQUIRE((op.out.coff * op.out.elem) % 16 == 0 && (op.out.cstride * op.out.elem) % 16 == 0,
+                    "conv_pair: output slice must be 16-byte aligned");
+        const int H = op.in.h, W = op.in.w, N = op.in.n;
+        if (op.pool) {
+            OPB_REQUIRE(H % 2 == 0 && W % 2 == 0 && op.relu, "conv_pair: fused pool needs even dims and ReLU");
+            OPB_REQUIRE(op.out.h == H / 2 && op.out.w == W / 2 && op.out.n == N, "conv_pair: pooled output dims");
+        } else {
+            OPB_REQUIRE(op.out.h == H && op.out.w == W && op.out.n == N, "conv_pair: output dims");
+        }
+        QProb& q = P.prob[i];
+        q.out = op.out.ptr();
+        q.bias = op.bias;
+        q.H = H; q.W = W; q.N = N;
+        q.tiles_x = cdiv(W, kTile);
+        q.tiles_y = cdiv(H, kTile);
+        q.m_tiles = q.tiles_x * q.tiles_y * N;
+        q.m_pairs = (q.m_tiles + 1) / 2;
+        q.out_cstride = op.out.cstride;
+        q.cout_store = op.cout_store;
+        q.n_tiles_n = op.cout_pad / block_n;
+        q.cin_chunks = op.in.c / 64;
+        q.pair_begin = pairs;
+        q.flags = (op.relu ? FLAG_RELU : 0) | (op.out.elem == 4 ? FLAG_F32 : 0) | (op.pool ? FLAG_POOL : 0);
+        pairs += q.m_pairs * q.n_tiles_n;
+
+        cuuint64_t adims[4] = {(cuuint64_t)op.in.c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+        cuuint64_t astr[3] = {(cuuint64_t)op.in.cstride * 2, (cuuint64_t)op.in.cstride * 2 * W,
+                              (cuuint64_t)op.in.cstride * 2 * W * H};
+        cuuint32_t abox[4] = {64, (cuuint32_t)kPitch, (cuuint32_t)(kTile + P.ks - 1), 1};
+        tensor_map_encode_bf16(&P.tmA[i], op.in.ptr(), 4, adims, astr, abox);
+        const cuuint64_t K = (cuuint64_t)op.ks * op.ks * op.in.c;
+        cuuint64_t wdims[2] = {K, (cuuint64_t)op.cout_pad};
+        cuuint64_t wstr[1] = {K * 2};
+        cuuint32_t wbox[2] = {64, (cuuint32_t)(block_n / 2)};
+        tensor_map_encode_bf16(&P.tmW[i], (void*)op.w, 2, wdims, wstr, wbox);
+    }
+    P.total_pairs = pairs;
+    L->tiles = pairs * 2;
+    L->block_n = block_n;
+    const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
+    L->grid = clusters * 2;
+    return L.release();
+}
+
+}  // namespace opb

@@ -209,7 +209,7 @@ struct Builder {
     opb_net* net;
     NetPlan* plan;
     bool fuse_pool;
-    int conv_impl;          // -1: per-tap tiles everywhere, 0 / 1: patch-resident MODE 0 / 1 for ks > 1
+    int conv_impl;          // -1: per-tap tiles everywhere, 0 / 1: patch-resident MODE 0 / 1, 2: CTA-pair kernel (ks > 1)
     TensorView act(int n, int h, int w, int c, int elem = 2, bool zero = false) {
         TensorView t;
         t.n = n; t.h = h; t.w = w; t.c = c; t.cstride = c; t.coff = 0; t.elem = elem;
@@ -249,8 +249,9 @@ struct Builder {
                 ops.push_back(op);
             }
             // 3x3 / 7x7 layers run patch-resident (conv_patch.cu); 1x1 layers (and OPB_CONV_IMPL=tap) per-tap tiles
-            ConvLaunch* L = (ops[0].ks > 1 && conv_impl >= 0) ? conv_patch_plan(ops, bn, net->ctx->num_sms, conv_impl)
-                                                             : conv_tc_plan(ops, bn, net->ctx->num_sms);
+            ConvLaunch* L = (ops[0].ks > 1 && conv_impl == 2) ? conv_pair_plan(ops, bn, net->ctx->num_sms)
+                            : (ops[0].ks > 1 && conv_impl >= 0) ? conv_patch_plan(ops, bn, net->ctx->num_sms, conv_impl)
+                                                                : conv_tc_plan(ops, bn, net->ctx->num_sms);
             plan->launches.push_back(L);
             plan->steps.push_back([L](cudaStream_t s) { conv_tc_plan_run(L, s); });
             plan->step_names.push_back(std::string(bn == 128 ? "conv_tc128:" : "conv_tc64:") + names[first]);
@@ -277,6 +278,7 @@ int default_conv_impl() {
     if (e && !strcmp(e, "tap")) return -1;
     if (e && !strcmp(e, "patch0")) return 0;
     if (e && !strcmp(e, "patch1")) return 1;
+    if (e && !strcmp(e, "pair")) return 2;
     return kDefaultConvImpl;
 }
 

@@ -122,7 +122,7 @@ struct NetPlan {
 };
 std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape>& shapes);
 void finalize_net(opb_net* net);
-constexpr int kDefaultConvImpl = 1;       // measured on B200 (bench.py, 720p 4-scale): patch MODE 1 1037 TFLOP/s, MODE 0 945, per-tap 948
+constexpr int kDefaultConvImpl = 2;       // measured on B200 (bench.py, 720p 4-scale, same box): CTA pair 3.60 ms of conv per frame, patch MODE 1 3.79, MODE 0 and per-tap slower
 int default_conv_impl();
 
 // cubic tap tables (host)

@@ -39,7 +39,7 @@ CASES = [
 ]
 
 
-IMPLS = {"tap": 2, "patch0": 3, "patch1": 4}       # per-tap tiles / patch-resident MODE 0 / MODE 1 (opb_conv2d impl)
+IMPLS = {"tap": 2, "patch0": 3, "patch1": 4, "pair": 5}       # per-tap tiles / patch-resident MODE 0 / MODE 1 (opb_conv2d impl)
 
 
 @pytest.mark.parametrize("impl", sorted(IMPLS))
