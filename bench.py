@@ -4,8 +4,9 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--frames-per-step F]
 
 A step is one pass of the whole Body path (preprocess at 4 scales -> CNN -> upsample/average -> Gaussian+NMS ->
-PAF scoring / matching / assembly) over a batch of F synthetic 1280x720 frames on every rank; frames are
-independent, so ranks never exchange data (weak scaling, no collective on the data path).  Rank 0 prints ONE
+PAF scoring / matching / assembly) over F synthetic 1280x720 frames on every rank, submitted as F/B batches of B
+frames (one launch per CNN layer per batch) round-robin over a few streams; frames are independent, so ranks never
+exchange data (weak scaling, no collective on the data path).  Rank 0 prints ONE
 JSON line.  `value` is measured with the frames already resident in HBM; `e2e` goes through the same public
 `Body` API with pinned HOST frames, the host->device copy of every frame and the device->host read of every
 result inside the timed region.  `--impl reference` times the CPU restatement of the reference (oracle/) on the
@@ -27,7 +28,7 @@ H, W = 720, 1280
 SCALES = (0.5, 1.0, 1.5, 2.0)
 METRIC = "body_pose_frames_per_sec_720p_4scale"
 GFLOP_PER_FRAME = 3634.8          # algorithmic conv FLOPs of the body net at the four padded sizes
-POOL_FRAMES = 64                  # 64 x 2.76 MB = 177 MB of distinct inputs (> 126 MB L2)
+POOL_FRAMES = 80                  # 80 x 2.76 MB = 221 MB of distinct inputs (> 126 MB L2)
 
 
 def rank_info():
@@ -167,22 +168,26 @@ def run_ours(args):
     host_np = frames_host.numpy()
     torch.cuda.synchronize()
 
+    B = args.batch
+    assert F % B == 0 and POOL_FRAMES % B == 0, "frames-per-step and the frame pool must be multiples of --batch"
+
     def step(step_idx, device_resident):
+        """F frames as F/B batches of B consecutive pool frames, round-robin over the sessions (streams)."""
         inflight = [False] * len(sessions)
-        for f in range(F):
-            si = f % len(sessions)
-            if inflight[si]:
-                body.collect(sessions[si])
-            idx = (step_idx * F + f) % POOL_FRAMES
-            if device_resident:
-                body.submit((frames_dev[idx].data_ptr(), (H, W)), sessions[si], where=1)
-            else:
-                body.submit(host_np[idx], sessions[si], where=2)
-            inflight[si] = True
         out = None
+        for b in range(F // B):
+            si = b % len(sessions)
+            if inflight[si]:
+                out = body.collect_batch(sessions[si])
+            idx = (step_idx * F + b * B) % POOL_FRAMES
+            if device_resident:
+                body.submit_batch((frames_dev[idx].data_ptr(), (B, H, W)), sessions[si], where=1)
+            else:
+                body.submit_batch(host_np[idx:idx + B], sessions[si], where=2)
+            inflight[si] = True
         for si, fl in enumerate(inflight):
             if fl:
-                out = body.collect(sessions[si])
+                out = body.collect_batch(sessions[si])
         return out
 
     def timed(device_resident):
@@ -216,7 +221,7 @@ def run_ours(args):
         s0.set_profiling(True)
         tc_ms, tc_gf, tc_n, n_prof = 0.0, 0.0, 0, 8
         for i in range(n_prof):
-            body.submit((frames_dev[i].data_ptr(), (H, W)), s0, where=1)
+            body.submit((frames_dev[i].data_ptr(), (H, W)), s0, where=1)     # single frames: per-launch numbers
             body.collect(s0)
             for name, ms, gf in s0.profile():
                 key = name.split(":")[0]
@@ -262,13 +267,14 @@ def run_ours(args):
 
     if rank == 0:
         total_frames = F * K * world
-        d2h = F * (4 * 25 + 2048 * 32 + 128 * 160)
+        d2h = F * (4 * 25 + 2048 * 32 + 128 * 160)          # per frame: counts + eager candidate / subset rows
         line = {"metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "Body() 4-scale [0.5,1.0,1.5,2.0] on synthetic 1280x720 frames, random-init bodypose_model",
-                           "frames_per_step": F, "streams": len(sessions), "parallelism": "frame-sharded replicas x%d" % world,
-                           "l2": "pool of %d distinct frames (177 MB) and ~1 GB of activations per frame exceed the 126 MB L2" % POOL_FRAMES},
+                           "frames_per_step": F, "frames_per_batch": B, "streams": len(sessions),
+                           "parallelism": "frame-sharded replicas x%d" % world,
+                           "l2": "pool of %d distinct frames (221 MB) and ~1 GB of activations per frame exceed the 126 MB L2" % POOL_FRAMES},
                 "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W * 3,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
@@ -284,7 +290,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=16)
+    ap.add_argument("--frames-per-step", type=int, default=32)
+    ap.add_argument("--batch", type=int, default=8, help="frames per batched submit (one launch per CNN layer per batch)")
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--layers", default=None, help="write the per-launch profile of one frame to this CSV")

@@ -95,10 +95,20 @@ int opb_body_submit(opb_session* s, const uint8_t* img_bgr, int img_is_device, i
                     const double* scale_search, int n_scales);
 int opb_body_wait(opb_session* s, int* n_candidate, int* n_subset);
 int opb_body_fetch(opb_session* s, double* candidate, int candidate_rows, double* subset, int subset_rows);
+/* Batched form (the reference's own throughput path batches frames too: srcmx/Batch_model.py:138-204): n_frames
+ * equally sized frames, contiguous (n, H, W, 3), go through every CNN layer in ONE launch per layer; results are
+ * per frame.  wait_batch fills n_candidate[n], n_subset[n] and (optionally) frame_status[n] (OPB_OK or
+ * OPB_ERR_SUBSET_INDEX per frame) and returns the first non-OK status.                                  */
+int opb_body_submit_batch(opb_session* s, const uint8_t* imgs_bgr, int img_is_device, int n_frames, int height,
+                          int width, const double* scale_search, int n_scales);
+int opb_body_wait_batch(opb_session* s, int* n_candidate, int* n_subset, int* frame_status);
+int opb_body_fetch_frame(opb_session* s, int frame, double* candidate, int candidate_rows, double* subset,
+                         int subset_rows);
 
 /* Copies the last finished frame's averaged maps to the host: heat (19, H, W) and paf (38, H, W) planar fp32 --
  * the heatmap_avg / paf_avg of src/body.py:33-34,67-68 -- so the reference's own post-processing can be run on
- * the device-produced maps (parity tests).  Either pointer may be NULL.                               */
+ * the device-produced maps (parity tests).  Either pointer may be NULL.  After a batch the buffers must hold all
+ * frames: (n, 19, H, W) and (n, 38, H, W).                                                             */
 int opb_body_maps(opb_session* s, float* host_heat, float* host_paf);
 
 /* ---- Hand.__call__ (src/hand.py:25-75) ----------------------------------------------------------

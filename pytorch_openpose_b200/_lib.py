@@ -44,6 +44,9 @@ SIGNATURES = {
     "opb_body_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_double), c_int]),
     "opb_body_wait": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int)]),
     "opb_body_fetch": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int]),
+    "opb_body_submit_batch": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_double), c_int]),
+    "opb_body_wait_batch": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
+    "opb_body_fetch_frame": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]),
     "opb_hand_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_double), c_int]),
     "opb_hand_wait": (c_int, [c_void_p, c_void_p]),
     "opb_body_maps": (c_int, [c_void_p, c_void_p, c_void_p]),

@@ -59,9 +59,53 @@ class Body(object):
         self.submit(oriImg)
         return self.collect()
 
+    # ---- batches of equally sized frames: one launch per CNN layer for the whole batch ----
+    def submit_batch(self, frames, session=None, where=0):
+        """frames: (n, H, W, 3) uint8 array (where 0 / 2) or (device pointer, (n, H, W)) (where 1)."""
+        s = session or self._session
+        if where == 1:
+            ptr, (n, H, W) = frames
+        else:
+            arr = np.ascontiguousarray(frames, dtype=np.uint8)
+            if arr.ndim != 4 or arr.shape[3] != 3:
+                raise ValueError("expected an (n, H, W, 3) uint8 BGR array")
+            if arr.shape[1] == 0:
+                raise ZeroDivisionError("float division by zero")
+            s._keepalive = arr
+            ptr, (n, H, W) = arr.ctypes.data, arr.shape[:3]
+        s._batch = n
+        arr_s, ns = _lib.scales_array(self.scale_search)
+        _lib.check(_lib.lib().opb_body_submit_batch(s.handle, ptr, where, n, H, W, arr_s, ns))
+
+    def collect_batch(self, session=None):
+        """-> list of (candidate, subset), one per frame.  Raises IndexError if any frame hit the reference's
+        src/body.py:173 edge (like calling the reference frame by frame would)."""
+        s = session or self._session
+        L = _lib.lib()
+        n = s._batch
+        nc, ns, st = (ctypes.c_int * n)(), (ctypes.c_int * n)(), (ctypes.c_int * n)()
+        _lib.check(L.opb_body_wait_batch(s.handle, nc, ns, st))
+        out = []
+        for f in range(n):
+            candidate = np.empty((nc[f], 4), dtype=np.float64)
+            subset = np.empty((ns[f], 20), dtype=np.float64)
+            _lib.check(L.opb_body_fetch_frame(s.handle, f, candidate.ctypes.data, nc[f], subset.ctypes.data, ns[f]))
+            out.append((np.array([]) if nc[f] == 0 else candidate, subset))
+        return out
+
+    def batch(self, frames):
+        self.submit_batch(frames)
+        return self.collect_batch()
+
     def last_maps(self, shape, session=None):
         """(heatmap_avg (H,W,19), paf_avg (H,W,38)) float32 of the last finished frame (src/body.py:67-68)."""
         s = session or self._session
+        if len(shape) == 4:                                  # (n, H, W, 3): maps of every frame of the last batch
+            n, H, W = shape[:3]
+            heat = np.empty((n, 19, H, W), dtype=np.float32)
+            paf = np.empty((n, 38, H, W), dtype=np.float32)
+            _lib.check(_lib.lib().opb_body_maps(s.handle, heat.ctypes.data, paf.ctypes.data))
+            return np.ascontiguousarray(heat.transpose(0, 2, 3, 1)), np.ascontiguousarray(paf.transpose(0, 2, 3, 1))
         H, W = shape[:2]
         heat = np.empty((19, H, W), dtype=np.float32)
         paf = np.empty((38, H, W), dtype=np.float32)

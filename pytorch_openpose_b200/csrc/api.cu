@@ -137,12 +137,15 @@ struct FramePlan {
     float* up_scratch = nullptr;
     float* heat_avg = nullptr;      // body: (19,H,W); hand: (n*22,H,W)
     float* paf_avg = nullptr;       // body: (38,H,W)
-    // body post-processing
-    PeakBuffers pb{};
-    int* part_count = nullptr;
-    LimbBuffers lb{};
-    int* order = nullptr;
-    unsigned char* used = nullptr;
+    // body post-processing, one set per frame of the batch
+    struct BodyPost {
+        PeakBuffers pb{};
+        int* part_count = nullptr;
+        LimbBuffers lb{};
+        int* order = nullptr;
+        unsigned char* used = nullptr;
+    };
+    std::vector<BodyPost> post;
     // hand post-processing
     HandBuffers hb{};
     int launches_per_frame = 0;
@@ -155,7 +158,7 @@ constexpr int kSubsetCapacity = 1024;
 constexpr int kEagerCand = 2048;      // rows copied to the host before the counts are known
 constexpr int kEagerSubset = 128;
 
-static void alloc_body_post(DevPool& pool, FramePlan& fp, int peak_cap, int pair_cap, int conn_cap, int subset_cap) {
+static void alloc_body_post(DevPool& pool, FramePlan::BodyPost& fp, int peak_cap, int pair_cap, int conn_cap, int subset_cap) {
     fp.pb.capacity = peak_cap;
     fp.pb.keys = pool.alloc_t<unsigned long long>(peak_cap);
     fp.pb.scores = pool.alloc_t<float>(peak_cap);
@@ -182,11 +185,14 @@ static void alloc_body_post(DevPool& pool, FramePlan& fp, int peak_cap, int pair
 
 using namespace opb;
 
-struct HostResults {                 // pinned
+struct HostResults {                 // pinned, one per frame of a body batch
     int counts[32];                  // [0] peaks appended, [1..19] part_begin, [20] subset rows, [21..24] status
     double cand[kEagerCand * 4];
     double subset[kEagerSubset * 20];
-    double hand_peaks[1];            // flexible tail (allocated to fit)
+};
+struct FrameResult {                 // host-side view of one finished frame
+    int n_cand = 0, n_subset = 0, status = 0;
+    std::vector<double> cand_all, subset_all;   // filled by wait() when the eager copy was too small
 };
 
 struct opb_session {
@@ -195,12 +201,13 @@ struct opb_session {
     cudaEvent_t done = nullptr;
     std::map<FrameKey, std::unique_ptr<FramePlan>> plans;
     FramePlan* active = nullptr;
-    HostResults* host = nullptr;     // pinned
-    size_t host_bytes = 0;
+    HostResults* host = nullptr;     // pinned, [frames]
+    double* hand_host = nullptr;     // pinned, [crops][21][3]
+    size_t host_bytes = 0, hand_host_bytes = 0;
+    std::vector<FrameResult> results;
+    int n_frames = 0;
     uint8_t* staging = nullptr;      // pinned image staging
     size_t staging_bytes = 0;
-    std::vector<double> cand_all, subset_all;   // filled by wait() when the eager copy was too small
-    int n_cand = 0, n_subset = 0, status = 0;
     int hand_crops = 0;
     Profiler prof;
     cudaEvent_t marks[2] = {nullptr, nullptr};
@@ -210,6 +217,7 @@ struct opb_session {
         plans.clear();
         net_plans.clear();
         if (host) cudaFreeHost(host);
+        if (hand_host) cudaFreeHost(hand_host);
         if (staging) cudaFreeHost(staging);
         if (done) cudaEventDestroy(done);
         for (auto m : marks) if (m) cudaEventDestroy(m);
@@ -219,12 +227,19 @@ struct opb_session {
 
 namespace opb {
 
-static void ensure_host(opb_session* s, size_t hand_doubles) {
-    const size_t need = sizeof(HostResults) + hand_doubles * sizeof(double);
-    if (s->host_bytes >= need) return;
-    if (s->host) cudaFreeHost(s->host);
-    OPB_CUDA(cudaMallocHost((void**)&s->host, need));
-    s->host_bytes = need;
+static void ensure_host(opb_session* s, int frames, size_t hand_doubles) {
+    const size_t need = sizeof(HostResults) * (size_t)frames;
+    if (s->host_bytes < need) {
+        if (s->host) cudaFreeHost(s->host);
+        OPB_CUDA(cudaMallocHost((void**)&s->host, need));
+        s->host_bytes = need;
+    }
+    const size_t hneed = hand_doubles * sizeof(double);
+    if (s->hand_host_bytes < hneed) {
+        if (s->hand_host) cudaFreeHost(s->hand_host);
+        OPB_CUDA(cudaMallocHost((void**)&s->hand_host, hneed));
+        s->hand_host_bytes = hneed;
+    }
 }
 static void ensure_staging(opb_session* s, size_t bytes) {
     if (s->staging_bytes >= bytes) return;
@@ -258,10 +273,12 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     fp->up_scratch = fp->pool.alloc_t<float>(scratch);
     fp->launches_per_frame = n_scales /*preprocess*/ + fp->net->kernel_launches;
     if (body) {
-        fp->heat_avg = fp->pool.alloc_t<float>((size_t)19 * H * W);
-        fp->paf_avg = fp->pool.alloc_t<float>((size_t)38 * H * W);
-        alloc_body_post(fp->pool, *fp, kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
-        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + 1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/;
+        fp->heat_avg = fp->pool.alloc_t<float>((size_t)n * 19 * H * W);
+        fp->paf_avg = fp->pool.alloc_t<float>((size_t)n * 38 * H * W);
+        fp->post.resize(n);
+        for (int f = 0; f < n; ++f)
+            alloc_body_post(fp->pool, fp->post[f], kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
+        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/);
     } else {
         fp->heat_avg = fp->pool.alloc_t<float>((size_t)n * 22 * H * W);
         fp->hb.labels = fp->pool.alloc_t<int>((size_t)n * 21 * H * W);
@@ -319,72 +336,102 @@ static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int
     upsample_avg_launch2(us, S, n, C, H, W, fp->up_scratch, out, st);
 }
 
-static void body_submit(opb_session* s, const uint8_t* img, int where, int H, int W, const double* scales, int ns) {
+static void body_submit(opb_session* s, const uint8_t* img, int where, int n, int H, int W, const double* scales, int ns) {
     OPB_REQUIRE(s->net->kind == OPB_NET_BODY, "session was created on a hand network");
+    OPB_REQUIRE(n >= 1 && n <= 64, "1..64 frames per batch");
     OPB_CUDA(cudaSetDevice(s->net->ctx->device));
-    FramePlan* fp = get_plan(s, 1, H, W, scales, ns);
-    ensure_host(s, 0);
+    FramePlan* fp = get_plan(s, n, H, W, scales, ns);
+    ensure_host(s, n, 0);
     s->active = fp;
+    s->n_frames = n;
     cudaStream_t st = s->stream;
     s->prof.reset();
     s->prof.mark(st, "start");
-    upload_image(s, fp, img, where, (size_t)H * W * 3);
+    upload_image(s, fp, img, where, (size_t)n * H * W * 3);
     s->prof.mark(st, "h2d");
-    run_front(s, fp, 1, H, W);
-    run_upsample(fp, false, 1, 19, 24, H, W, fp->heat_avg, st);
-    run_upsample(fp, true, 1, 38, 40, H, W, fp->paf_avg, st);
+    run_front(s, fp, n, H, W);
+    run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
+    run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
     s->prof.mark(st, "upsample_avg");
-    smooth_nms_launch(fp->heat_avg, H, W, 18, 0.1, fp->pb, nullptr, st);            // thre1, src/body.py:30
-    s->prof.mark(st, "smooth_nms");
-    sort_peaks_launch2(fp->pb, 18, fp->part_count, st);
-    s->prof.mark(st, "sort_peaks");
-    paf_group_launch2(fp->paf_avg, H, W, fp->pb.candidates, fp->pb.part_begin, fp->lb, 0.05, fp->order, fp->used,
-                      fp->pb.capacity, st);                                          // thre2, src/body.py:31
-    s->prof.mark(st, "paf_group");
-    HostResults* h = s->host;
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[0], fp->pb.count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[1], fp->pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[20], fp->lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[21], fp->lb.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(h->cand, fp->pb.candidates, sizeof(h->cand), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(h->subset, fp->lb.subset, sizeof(h->subset), cudaMemcpyDeviceToHost, st));
-    s->prof.mark(st, "d2h");
+    const size_t px = (size_t)H * W;
+    for (int f = 0; f < n; ++f) {
+        FramePlan::BodyPost& bp = fp->post[f];
+        smooth_nms_launch(fp->heat_avg + f * 19 * px, H, W, 18, 0.1, bp.pb, nullptr, st);          // thre1, src/body.py:30
+        s->prof.mark(st, "smooth_nms");
+        sort_peaks_launch2(bp.pb, 18, bp.part_count, st);
+        s->prof.mark(st, "sort_peaks");
+        paf_group_launch2(fp->paf_avg + f * 38 * px, H, W, bp.pb.candidates, bp.pb.part_begin, bp.lb, 0.05, bp.order,
+                          bp.used, bp.pb.capacity, st);                                            // thre2, src/body.py:31
+        s->prof.mark(st, "paf_group");
+        HostResults* h = s->host + f;
+        OPB_CUDA(cudaMemcpyAsync(&h->counts[0], bp.pb.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OPB_CUDA(cudaMemcpyAsync(&h->counts[1], bp.pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        OPB_CUDA(cudaMemcpyAsync(&h->counts[20], bp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+        OPB_CUDA(cudaMemcpyAsync(&h->counts[21], bp.lb.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+        OPB_CUDA(cudaMemcpyAsync(h->cand, bp.pb.candidates, sizeof(h->cand), cudaMemcpyDeviceToHost, st));
+        OPB_CUDA(cudaMemcpyAsync(h->subset, bp.lb.subset, sizeof(h->subset), cudaMemcpyDeviceToHost, st));
+        s->prof.mark(st, "d2h");
+    }
     OPB_CUDA(cudaEventRecord(s->done, st));
     s->net->ctx->launches += fp->launches_per_frame;
 }
 
-static int body_wait(opb_session* s, int* n_cand, int* n_subset) {
+// returns the first non-OK per-frame status (OPB_ERR_SUBSET_INDEX mirrors the reference's IndexError)
+static int body_wait(opb_session* s, int* n_cand, int* n_subset, int* frame_status) {
     OPB_REQUIRE(s->active != nullptr, "no frame in flight");
     FramePlan* fp = s->active;
     OPB_CUDA(cudaEventSynchronize(s->done));
-    HostResults* h = s->host;
-    const int appended = h->counts[0];
-    const int status = h->counts[21];
-    if (appended > fp->pb.capacity)
-        throw Error(OPB_ERR_CAPACITY, "more than " + std::to_string(fp->pb.capacity) + " heat-map peaks in one frame");
-    if (status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))
-        throw Error(OPB_ERR_CAPACITY, "limb / person buffers overflowed (status " + std::to_string(status) + ")");
-    s->n_cand = h->counts[19];           // part_begin[18] = total
-    s->n_subset = h->counts[20];
-    s->status = status;
-    s->cand_all.clear();
-    s->subset_all.clear();
-    if (s->n_cand > kEagerCand) {
-        s->cand_all.resize((size_t)s->n_cand * 4);
-        OPB_CUDA(cudaMemcpyAsync(s->cand_all.data(), fp->pb.candidates, s->cand_all.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+    s->results.assign(s->n_frames, FrameResult());
+    int rc = OPB_OK;
+    bool extra = false;
+    for (int f = 0; f < s->n_frames; ++f) {
+        HostResults* h = s->host + f;
+        FramePlan::BodyPost& bp = fp->post[f];
+        FrameResult& r = s->results[f];
+        const int appended = h->counts[0];
+        const int status = h->counts[21];
+        if (appended > bp.pb.capacity)
+            throw Error(OPB_ERR_CAPACITY, "more than " + std::to_string(bp.pb.capacity) + " heat-map peaks in one frame");
+        if (status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))
+            throw Error(OPB_ERR_CAPACITY, "limb / person buffers overflowed (status " + std::to_string(status) + ")");
+        r.n_cand = h->counts[19];            // part_begin[18] = total
+        r.n_subset = h->counts[20];
+        r.status = (status & kStIndexError) ? OPB_ERR_SUBSET_INDEX : OPB_OK;
+        if (r.n_cand > kEagerCand) {
+            r.cand_all.resize((size_t)r.n_cand * 4);
+            OPB_CUDA(cudaMemcpyAsync(r.cand_all.data(), bp.pb.candidates, r.cand_all.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+            extra = true;
+        }
+        if (r.n_subset > kEagerSubset) {
+            r.subset_all.resize((size_t)r.n_subset * 20);
+            OPB_CUDA(cudaMemcpyAsync(r.subset_all.data(), bp.lb.subset, r.subset_all.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+            extra = true;
+        }
+        if (n_cand) n_cand[f] = r.n_cand;
+        if (n_subset) n_subset[f] = r.n_subset;
+        if (frame_status) frame_status[f] = r.status;
+        if (r.status != OPB_OK && rc == OPB_OK) rc = r.status;
     }
-    if (s->n_subset > kEagerSubset) {
-        s->subset_all.resize((size_t)s->n_subset * 20);
-        OPB_CUDA(cudaMemcpyAsync(s->subset_all.data(), fp->lb.subset, s->subset_all.size() * 8, cudaMemcpyDeviceToHost, s->stream));
-    }
-    if (!s->cand_all.empty() || !s->subset_all.empty()) OPB_CUDA(cudaStreamSynchronize(s->stream));
-    *n_cand = s->n_cand;
-    *n_subset = s->n_subset;
-    if (status & kStIndexError) {
+    if (extra) OPB_CUDA(cudaStreamSynchronize(s->stream));
+    if (rc == OPB_ERR_SUBSET_INDEX)
         set_last_error("list assignment index out of range (three subset rows match one connection, src/body.py:173)");
-        return OPB_ERR_SUBSET_INDEX;
+    return rc;
+}
+
+static void body_fetch(opb_session* s, int frame, double* candidate, int cand_rows, double* subset, int subset_rows) {
+    OPB_REQUIRE(s->active && frame >= 0 && frame < (int)s->results.size(), "no finished frame with this index");
+    const FrameResult& r = s->results[frame];
+    if (cand_rows < r.n_cand || subset_rows < r.n_subset) throw Error(OPB_ERR_CAPACITY, "fetch buffers smaller than the result");
+    if (r.n_cand) {
+        OPB_REQUIRE(candidate != nullptr, "null candidate buffer");
+        const double* src = r.cand_all.empty() ? s->host[frame].cand : r.cand_all.data();
+        memcpy(candidate, src, (size_t)r.n_cand * 4 * sizeof(double));
     }
-    return OPB_OK;
+    if (r.n_subset) {
+        OPB_REQUIRE(subset != nullptr, "null subset buffer");
+        const double* src = r.subset_all.empty() ? s->host[frame].subset : r.subset_all.data();
+        memcpy(subset, src, (size_t)r.n_subset * 20 * sizeof(double));
+    }
 }
 
 static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, int H, int W, const double* scales, int ns) {
@@ -392,7 +439,7 @@ static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, in
     OPB_REQUIRE(n >= 1 && n <= 1024, "1..1024 crops per batch");
     OPB_CUDA(cudaSetDevice(s->net->ctx->device));
     FramePlan* fp = get_plan(s, n, H, W, scales, ns);
-    ensure_host(s, (size_t)n * 63);
+    ensure_host(s, 1, (size_t)n * 63);
     s->active = fp;
     s->hand_crops = n;
     cudaStream_t st = s->stream;
@@ -405,7 +452,7 @@ static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, in
     s->prof.mark(st, "upsample_avg");
     hand_peaks_launch2(fp->heat_avg, n, 22, H, W, 0.03, fp->hb, nullptr, st);        // thre, src/hand.py:31
     s->prof.mark(st, "hand_peaks");
-    OPB_CUDA(cudaMemcpyAsync(s->host->hand_peaks, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(s->hand_host, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
     s->prof.mark(st, "d2h");
     OPB_CUDA(cudaEventRecord(s->done, st));
     s->net->ctx->launches += fp->launches_per_frame;
@@ -521,33 +568,38 @@ int opb_session_destroy(opb_session* s) {
 int opb_body_submit(opb_session* s, const uint8_t* img, int img_is_device, int H, int W, const double* scales, int ns) {
     return guarded([&] {
         OPB_REQUIRE(s && img && scales, "null argument");
-        body_submit(s, img, img_is_device, H, W, scales, ns);
+        body_submit(s, img, img_is_device, 1, H, W, scales, ns);
+    });
+}
+int opb_body_submit_batch(opb_session* s, const uint8_t* imgs, int img_is_device, int n_frames, int H, int W,
+                          const double* scales, int ns) {
+    return guarded([&] {
+        OPB_REQUIRE(s && imgs && scales, "null argument");
+        body_submit(s, imgs, img_is_device, n_frames, H, W, scales, ns);
     });
 }
 int opb_body_wait(opb_session* s, int* n_candidate, int* n_subset) {
     int rc = OPB_OK;
     int g = guarded([&] {
         OPB_REQUIRE(s && n_candidate && n_subset, "null argument");
-        rc = body_wait(s, n_candidate, n_subset);
+        OPB_REQUIRE(s->n_frames == 1, "a batch is in flight: use opb_body_wait_batch");
+        rc = body_wait(s, n_candidate, n_subset, nullptr);
+    });
+    return g != OPB_OK ? g : rc;
+}
+int opb_body_wait_batch(opb_session* s, int* n_candidate, int* n_subset, int* frame_status) {
+    int rc = OPB_OK;
+    int g = guarded([&] {
+        OPB_REQUIRE(s && n_candidate && n_subset, "null argument");
+        rc = body_wait(s, n_candidate, n_subset, frame_status);
     });
     return g != OPB_OK ? g : rc;
 }
 int opb_body_fetch(opb_session* s, double* candidate, int cand_rows, double* subset, int subset_rows) {
-    return guarded([&] {
-        OPB_REQUIRE(s && s->active, "no finished frame");
-        if (cand_rows < s->n_cand || subset_rows < s->n_subset)
-            throw Error(OPB_ERR_CAPACITY, "fetch buffers smaller than the result");
-        if (s->n_cand) {
-            OPB_REQUIRE(candidate != nullptr, "null candidate buffer");
-            const double* src = s->cand_all.empty() ? s->host->cand : s->cand_all.data();
-            memcpy(candidate, src, (size_t)s->n_cand * 4 * sizeof(double));
-        }
-        if (s->n_subset) {
-            OPB_REQUIRE(subset != nullptr, "null subset buffer");
-            const double* src = s->subset_all.empty() ? s->host->subset : s->subset_all.data();
-            memcpy(subset, src, (size_t)s->n_subset * 20 * sizeof(double));
-        }
-    });
+    return guarded([&] { body_fetch(s, 0, candidate, cand_rows, subset, subset_rows); });
+}
+int opb_body_fetch_frame(opb_session* s, int frame, double* candidate, int cand_rows, double* subset, int subset_rows) {
+    return guarded([&] { body_fetch(s, frame, candidate, cand_rows, subset, subset_rows); });
 }
 
 int opb_session_set_profiling(opb_session* s, int on) {
@@ -591,7 +643,7 @@ int opb_body_maps(opb_session* s, float* host_heat, float* host_paf) {
     return guarded([&] {
         OPB_REQUIRE(s && s->active && s->net->kind == OPB_NET_BODY, "no finished body frame");
         OPB_CUDA(cudaEventSynchronize(s->done));
-        const size_t px = (size_t)s->active->key.H * s->active->key.W;
+        const size_t px = (size_t)s->active->key.H * s->active->key.W * s->active->key.n;     // all frames of a batch
         if (host_heat) OPB_CUDA(cudaMemcpy(host_heat, s->active->heat_avg, px * 19 * 4, cudaMemcpyDeviceToHost));
         if (host_paf) OPB_CUDA(cudaMemcpy(host_paf, s->active->paf_avg, px * 38 * 4, cudaMemcpyDeviceToHost));
     });
@@ -615,7 +667,7 @@ int opb_hand_wait(opb_session* s, double* peaks) {
     return guarded([&] {
         OPB_REQUIRE(s && s->active && peaks, "no frame in flight");
         OPB_CUDA(cudaEventSynchronize(s->done));
-        memcpy(peaks, s->host->hand_peaks, (size_t)s->hand_crops * 63 * sizeof(double));
+        memcpy(peaks, s->hand_host, (size_t)s->hand_crops * 63 * sizeof(double));
     });
 }
 
@@ -735,7 +787,7 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int H, int W, const 
         OPB_REQUIRE(dev_paf && dev_candidates && host_part_begin19 && host_subset && n_subset, "null argument");
         OPB_CUDA(cudaSetDevice(ctx->device));
         DevPool pool;
-        FramePlan fp;
+        FramePlan::BodyPost fp;
         const int total = host_part_begin19[18];
         int max_part = 1;
         for (int p = 0; p < 18; ++p) max_part = std::max(max_part, host_part_begin19[p + 1] - host_part_begin19[p]);

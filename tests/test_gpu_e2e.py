@@ -130,3 +130,19 @@ def test_synthetic_scene_through_public_api_grouping(golden):
     assert len(cand) == 900 and np.array_equal(cand, g["cand_p50"]) and np.array_equal(subset, g["subset_p50"])
     total_pairs = sum((pb[a] - pb[a - 1]) * (pb[b] - pb[b - 1]) for a, b in O.LIMB_SEQ)
     assert total_pairs == 47500
+
+
+def test_body_batch_equals_frame_by_frame():
+    """Batched frames (one launch per layer for the whole batch) give exactly the per-frame results."""
+    from pytorch_openpose_b200 import Body
+    sd = O.make_weights("body", 0)
+    frames = np.random.default_rng(11).integers(0, 256, (3, 120, 160, 3), dtype=np.uint8)
+    body = Body(sd, scale_search=[0.5, 1.0])
+    batched = body.batch(frames)
+    heat, paf = body.last_maps(frames.shape)
+    assert len(batched) == 3
+    for f in range(3):
+        c1, s1 = body(frames[f])
+        assert np.array_equal(batched[f][0], c1) and np.array_equal(batched[f][1], s1)
+        rc, rs = O.body_postprocess(heat[f].astype(np.float64), paf[f].astype(np.float64), 120)
+        assert np.array_equal(batched[f][0], rc) and np.array_equal(batched[f][1], rs)
