@@ -79,7 +79,13 @@ def test_hand_kaiming_matches_golden_within_1px(golden):
     print("hand maps rel err vs fp32 oracle: %.3e" % _rel(maps, ravg))
     ref = g["peaks"]
     both = (ref[:, 2] > 0) & (peaks[:, 2] > 0)
-    print("hand: %d/%d key points found by both" % (both.sum(), (ref[:, 2] > 0).sum()))
+    dist = np.abs(ref[both, :2] - peaks[both, :2]).max(1) if both.any() else np.zeros(0)
+    print("hand: %d/%d key points found by both, max |dx|,|dy| = %s px" % (both.sum(), (ref[:, 2] > 0).sum(),
+                                                                         dist.max() if len(dist) else None))
+    # north_star (3): key points within 1 px of the REAL reference's recorded output, end to end (bf16 device
+    # network + IPP-free resize vs the reference's fp32 CPU network + cv2)
+    assert both.sum() == (ref[:, 2] > 0).sum() == (peaks[:, 2] > 0).sum()
+    assert (dist <= 1.0).all()
 
 
 def test_hand_batch_equals_single():
@@ -146,3 +152,33 @@ def test_body_batch_equals_frame_by_frame():
         assert np.array_equal(batched[f][0], c1) and np.array_equal(batched[f][1], s1)
         rc, rs = O.body_postprocess(heat[f].astype(np.float64), paf[f].astype(np.float64), 120)
         assert np.array_equal(batched[f][0], rc) and np.array_equal(batched[f][1], rs)
+
+
+def _match_rate(cand_dev, cand_ref):
+    """Fraction of reference key points that have a device key point within 1 px (Chebyshev)."""
+    if len(cand_ref) == 0:
+        return 1.0, 0
+    if len(cand_dev) == 0:
+        return 0.0, len(cand_ref)
+    d = np.abs(cand_ref[:, None, :2] - cand_dev[None, :, :2]).max(-1)
+    return float((d.min(1) <= 1.0).mean()), len(cand_ref)
+
+
+@pytest.mark.parametrize("init,seed", [("kaiming", 2)])
+def test_body_end_to_end_keypoints_within_1px(init, seed):
+    """north_star (3): end-to-end key points of the device path vs the fp32 CPU path (cv2 resize, fp32 convs).
+    Only weights that give maps with spatial structure are meaningful here: with PyTorch's default init the maps
+    are constant to ~1e-4 and their "peaks" are rounding noise of whichever arithmetic produced them
+    (measured: 18 % of the fp32 path's noise peaks reappear within 1 px), so that configuration is judged by
+    criteria (1) and (2) in test_body_c1_default_init instead."""
+    import cv2
+    from pytorch_openpose_b200 import Body
+    sd = O.make_weights("body", seed, init)
+    img = cv2.GaussianBlur(np.random.default_rng(21).integers(0, 256, (240, 320, 3), dtype=np.uint8), (0, 0), 3)
+    body = Body(sd, scale_search=[0.5, 1.0])
+    cand, subset = body(img)
+    rc, rs = O.body_call(img, sd, (0.5, 1.0), use_cv2=True)
+    rate, n = _match_rate(cand.reshape(-1, 4), rc.reshape(-1, 4))
+    print("%s: %d reference key points, %d device key points, %.1f %% within 1 px" % (init, n, len(cand), 100 * rate))
+    # random-init maps have flat, noise-like maxima: a bf16 perturbation moves or merges some of them (DESIGN.md 2)
+    assert rate >= 0.8
