@@ -259,6 +259,24 @@ def run_ours(args):
                 "gflop_per_frame": tc_gf / (n_prof * B), "ms_per_frame": tc_ms / (n_prof * B),
                 "measured_over": "%d serialised profiled batches of %d frames after the timed region (CUDA events around every launch)" % (n_prof, B)}
 
+    # ---- BASELINE.json's second metric: PAF-grouping ms/frame on the crowded synthetic scene (50 people) ----
+    grouping = None
+    if rank == 0:
+        import ctypes
+        heat50, paf50, _ = O.synthetic_scene(H, W, (10, 5), seed=0)
+        d_heat = torch.from_numpy(np.ascontiguousarray(heat50.transpose(2, 0, 1), dtype=np.float32)).cuda()
+        d_paf = torch.from_numpy(np.ascontiguousarray(paf50.transpose(2, 0, 1), dtype=np.float32)).cuda()
+        torch.cuda.synchronize()
+        ms, nc, ns = ctypes.c_float(), ctypes.c_int(), ctypes.c_int()
+        _lib.check(_lib.lib().opb_bench_grouping(_lib.context(local), d_heat.data_ptr(), d_paf.data_ptr(), H, W, 50,
+                                                 ctypes.byref(ms), ctypes.byref(nc), ctypes.byref(ns)))
+        grouping = {"value": ms.value, "unit": "ms/frame", "candidates": nc.value, "persons": ns.value,
+                    "workload": "synthetic 1280x720 maps, 50 people, 47.5 k limb pairs: Gaussian + NMS + PAF scoring + matching + assembly"}
+        if not args.no_cpu_baseline:
+            t0 = time.perf_counter()
+            O.body_postprocess(heat50, paf50, H)
+            grouping["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -279,6 +297,7 @@ def run_ours(args):
                 "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W * 3,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
+                "paf_grouping": grouping,
                 "stage_ms_per_frame": {k: round(v, 4) for k, v in stages.items()}}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -146,6 +146,11 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int height, int widt
                     const int* host_part_begin19, double thre2, double* host_subset, int subset_capacity,
                     int* n_subset, double* host_connections /* optional 19*conn_cap*5 */, int conn_capacity,
                     int* host_conn_count19 /* optional */);
+/* Measurement helper for BASELINE.json's second metric ("PAF-grouping ms/frame"): times `iters` repetitions of
+ * src/body.py:70-212 (Gaussian + NMS + peak ordering + PAF scoring + matching + assembly) on resident device maps
+ * with CUDA events, buffers allocated once.                                                            */
+int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev_paf, int height, int width,
+                       int iters, float* ms_per_frame, int* n_candidate, int* n_subset);
 /* src/hand.py:59-75 on a planar (>=21, h, w) fp32 device map -> 21x3 float64 host array.            */
 int opb_hand_peaks(opb_context* ctx, const float* dev_heat, int height, int width, double thre, double* host_peaks);
 

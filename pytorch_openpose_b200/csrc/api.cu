@@ -818,6 +818,42 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int H, int W, const 
     return g != OPB_OK ? g : rc;
 }
 
+int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev_paf, int H, int W, int iters,
+                       float* ms_per_frame, int* n_candidate, int* n_subset) {
+    return guarded([&] {
+        OPB_REQUIRE(dev_heat && dev_paf && ms_per_frame && iters >= 1, "bad arguments");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool pool;
+        FramePlan::BodyPost bp;
+        alloc_body_post(pool, bp, kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
+        cudaEvent_t e0, e1;
+        OPB_CUDA(cudaEventCreate(&e0));
+        OPB_CUDA(cudaEventCreate(&e1));
+        auto once = [&] {
+            smooth_nms_launch(dev_heat, H, W, 18, 0.1, bp.pb, nullptr, ctx->stream);
+            sort_peaks_launch2(bp.pb, 18, bp.part_count, ctx->stream);
+            paf_group_launch2(dev_paf, H, W, bp.pb.candidates, bp.pb.part_begin, bp.lb, 0.05, bp.order, bp.used,
+                              bp.pb.capacity, ctx->stream);
+        };
+        for (int i = 0; i < 3; ++i) once();
+        OPB_CUDA(cudaEventRecord(e0, ctx->stream));
+        for (int i = 0; i < iters; ++i) once();
+        OPB_CUDA(cudaEventRecord(e1, ctx->stream));
+        OPB_CUDA(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        OPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        *ms_per_frame = ms / (float)iters;
+        ctx->launches += 6 * (iters + 3);
+        int pb19[19], ns = 0;
+        OPB_CUDA(cudaMemcpy(pb19, bp.pb.part_begin, sizeof(pb19), cudaMemcpyDeviceToHost));
+        OPB_CUDA(cudaMemcpy(&ns, bp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost));
+        if (n_candidate) *n_candidate = pb19[18];
+        if (n_subset) *n_subset = ns;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+    });
+}
+
 int opb_hand_peaks(opb_context* ctx, const float* dev_heat, int H, int W, double thre, double* host_peaks) {
     return guarded([&] {
         OPB_REQUIRE(dev_heat && host_peaks, "null argument");
