@@ -272,13 +272,13 @@ def run_ours(args):
                                                  ctypes.byref(ms), ctypes.byref(nc), ctypes.byref(ns)))
         grouping = {"value": ms.value, "unit": "ms/frame", "candidates": nc.value, "persons": ns.value,
                     "workload": "synthetic 1280x720 maps, 50 people, 47.5 k limb pairs: Gaussian + NMS + PAF scoring + matching + assembly"}
-        if not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline:
             t0 = time.perf_counter()
             O.body_postprocess(heat50, paf50, H)
             grouping["cpu_port_ms"] = 1e3 * (time.perf_counter() - t0)
 
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:        # reported at N=1 only
         threads = os.cpu_count() or 1
         t = cpu_reference_frames(2, threads)
         cpu = {"value": 2.0 / float(np.sum(t)), "unit": "frames/s", "cores": threads, "kind": "port",
