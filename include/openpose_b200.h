@@ -80,6 +80,7 @@ int opb_session_destroy(opb_session* s);
 int opb_session_set_profiling(opb_session* s, int on);
 int opb_session_profile_count(opb_session* s);
 int opb_session_profile_get(opb_session* s, int i, const char** name, float* ms_since_prev, double* gflop);
+int opb_session_progress(opb_session* s, int* last_done, int* total, const char** name_done, const char** name_next);
 int opb_session_mark(opb_session* s, int slot);
 int opb_session_elapsed(opb_session* a, int slot_a, opb_session* b, int slot_b, float* ms);
 

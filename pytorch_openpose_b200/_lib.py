@@ -39,6 +39,7 @@ SIGNATURES = {
     "opb_session_set_profiling": (c_int, [c_void_p, c_int]),
     "opb_session_profile_count": (c_int, [c_void_p]),
     "opb_session_profile_get": (c_int, [c_void_p, c_int, POINTER(c_char_p), POINTER(c_float), POINTER(c_double)]),
+    "opb_session_progress": (c_int, [c_void_p, POINTER(c_int), POINTER(c_int), POINTER(c_char_p), POINTER(c_char_p)]),
     "opb_session_mark": (c_int, [c_void_p, c_int]),
     "opb_session_elapsed": (c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(c_float)]),
     "opb_body_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_double), c_int]),
@@ -195,6 +196,12 @@ class Session(object):
             check(L.opb_session_profile_get(self.handle, i, ctypes.byref(name), ctypes.byref(ms), ctypes.byref(gf)))
             out.append((name.value.decode(), ms.value, gf.value))
         return out
+
+    def progress(self):
+        """(index of the last completed profile mark, total marks, its name, name of the next one) -- debugging."""
+        d, t, a, b = c_int(), c_int(), c_char_p(), c_char_p()
+        check(lib().opb_session_progress(self.handle, ctypes.byref(d), ctypes.byref(t), ctypes.byref(a), ctypes.byref(b)))
+        return d.value, t.value, (a.value or b"").decode(), (b.value or b"").decode()
 
     def mark(self, slot):
         check(lib().opb_session_mark(self.handle, slot))

@@ -254,6 +254,7 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     auto it = s->plans.find(key);
     if (it != s->plans.end()) return it->second.get();
     OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+    OPB_CUDA(cudaDeviceSynchronize());          // no other session's work in flight while buffers are created
     auto fp = std::make_unique<FramePlan>();
     fp->key = key;
     const bool body = s->net->kind == OPB_NET_BODY;
@@ -286,6 +287,9 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
         fp->hb.peaks = fp->pool.alloc_t<double>((size_t)n * 21 * 3, true);
         fp->launches_per_frame += (n_scales + 1) + 4;
     }
+    // Plan construction uses cudaMalloc / cudaMemset / cudaMemcpy on the legacy default stream, which does NOT order
+    // with the sessions' non-blocking streams: finish it (zero fills included) before any kernel of the plan runs.
+    OPB_CUDA(cudaDeviceSynchronize());
     FramePlan* raw = fp.get();
     s->plans[key] = std::move(fp);
     return raw;
@@ -621,6 +625,21 @@ int opb_session_profile_get(opb_session* s, int i, const char** name, float* ms_
         if (gflop) *gflop = s->prof.gflop[i];
     });
 }
+/* debug: name of the last profile mark of the in-flight frame that has completed (-1 / "" if none) */
+int opb_session_progress(opb_session* s, int* last_done, int* total, const char** name_done, const char** name_next) {
+    return guarded([&] {
+        OPB_REQUIRE(s && last_done && total, "null argument");
+        int done = -1;
+        for (int i = 0; i < (int)s->prof.used; ++i) {
+            if (cudaEventQuery(s->prof.ev[i]) == cudaSuccess) done = i;
+            else break;
+        }
+        *last_done = done;
+        *total = (int)s->prof.used;
+        if (name_done) *name_done = done >= 0 ? s->prof.names[done].c_str() : "";
+        if (name_next) *name_next = done + 1 < (int)s->prof.used ? s->prof.names[done + 1].c_str() : "";
+    });
+}
 /* timing marks on the session's stream (bench.py): slot 0/1 */
 int opb_session_mark(opb_session* s, int slot) {
     return guarded([&] {
@@ -702,7 +721,10 @@ int opb_net_forward(opb_session* s, const uint8_t* dev_in, int n, int hp, int wp
         OPB_CUDA(cudaSetDevice(s->net->ctx->device));
         std::vector<NetShape> shapes{{n, hp, wp}};
         auto& plan = s->net_plans[shapes];
-        if (!plan) plan = build_net_plan(s->net, shapes);
+        if (!plan) {
+            plan = build_net_plan(s->net, shapes);
+            OPB_CUDA(cudaDeviceSynchronize());      // zero fills of the plan run on the legacy default stream
+        }
         const size_t px = (size_t)n * (hp / 8) * (wp / 8);
         OPB_CUDA(cudaMemcpyAsync(plan->in_u8[0], dev_in, (size_t)n * hp * wp * 3, cudaMemcpyDeviceToDevice, s->stream));
         plan->run(s->stream);

@@ -144,6 +144,11 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
         }
         fence_barrier_init();
     }
+    // Both CTAs of the pair must be resident and past their start-up before either issues the paired TMEM
+    // allocation: a cta_group::2 alloc issued while the peer CTA is still being launched (its SM busy with blocks of
+    // another stream) left the late CTA's own alloc waiting forever (cuda-gdb: peer warp 1 parked in tcgen05.alloc,
+    // everybody else at the cluster barrier below).
+    cluster_sync_all();
     if (warp == 1) tmem_alloc_2sm(tmem_slot, C::kTmemCols);
     tc_fence_before();
     cluster_sync_all();                                 // barrier inits + TMEM allocation visible in both CTAs
@@ -322,6 +327,9 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
         tc_fence_after();
         tmem_dealloc_2sm(tmem_base, C::kTmemCols);
     }
+    // ... and nobody exits before BOTH CTAs have released their TMEM, so that the next cluster scheduled on this TPC
+    // never meets a half-released pair allocation.
+    cluster_sync_all();
 }
 
 struct PairLaunch : ConvLaunch {

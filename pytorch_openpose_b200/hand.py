@@ -47,8 +47,25 @@ class Hand(object):
         _lib.check(_lib.lib().opb_hand_maps(s.handle, heat.ctypes.data))
         return np.ascontiguousarray(heat.transpose(0, 2, 3, 1))
 
+    MAX_BATCH = 32          # crops per submit: ~0.7 GB of activations per 4-scale crop
+
     def __call__(self, oriImg):
         batched = np.ndim(oriImg) == 4
+        if batched and len(oriImg) > self.MAX_BATCH:
+            # large batches (BASELINE config 3: 256 crops) run as chunks, double-buffered over two sessions
+            if not hasattr(self, "_session2"):
+                self._session2 = self.net.session()
+            sessions = (self._session, self._session2)
+            out, pending = [], []
+            for i, lo in enumerate(range(0, len(oriImg), self.MAX_BATCH)):
+                s = sessions[i % 2]
+                if len(pending) == 2:
+                    out.append(self.collect(pending.pop(0)))
+                self.submit(oriImg[lo:lo + self.MAX_BATCH], s)
+                pending.append(s)
+            for s in pending:
+                out.append(self.collect(s))
+            return np.concatenate(out, 0)
         self.submit(oriImg)
         peaks = self.collect()
         return peaks if batched else peaks[0]
