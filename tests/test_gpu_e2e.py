@@ -34,6 +34,32 @@ def test_body_c1_default_init():
     assert cand.dtype == np.float64 and subset.dtype == np.float64 and subset.shape[1:] == (20,)
 
 
+@pytest.mark.parametrize("init,seed", [("torch_default", 0), ("kaiming", 2)])
+def test_body_c2_full_size(init, seed):
+    """BASELINE config 2 (the bench workload): 1280x720 frame, scale_search=[0.5,1,1.5,2].  Discrete results must be
+    identical to the reference post-processing on the device-produced maps; maps within 1e-2 of the CPU oracle."""
+    from pytorch_openpose_b200 import Body
+    sd = O.make_weights("body", seed, init=init)
+    if init == "kaiming":
+        import cv2
+        img = cv2.GaussianBlur(np.random.default_rng(21).integers(0, 256, (720, 1280, 3), dtype=np.uint8), (0, 0), 6)
+    else:
+        img = np.random.default_rng(0).integers(0, 256, (720, 1280, 3), dtype=np.uint8)
+    scales = [0.5, 1.0, 1.5, 2.0]
+    body = Body(sd, scale_search=scales)
+    cand, subset = body(img)
+    heat, paf = body.last_maps(img.shape)
+    rc, rs = O.body_postprocess(heat.astype(np.float64), paf.astype(np.float64), 720)
+    assert cand.shape == rc.shape and np.array_equal(cand, rc)
+    assert subset.shape == rs.shape and np.array_equal(subset, rs)
+    if init == "torch_default":
+        # (the reference's own count at this config is 220 noise peaks, SURVEY.md appendix C.7: default-init maps are
+        #  flat to ~1e-4, so which pixels are "maxima" is rounding noise of the arithmetic, here bf16 -- DESIGN.md 2)
+        assert subset.shape == (0, 20)
+        _, _, rheat, rpaf = O.body_call(img, sd, tuple(scales), use_cv2=True, return_maps=True)
+        assert _rel(heat, rheat) <= 1e-2 and _rel(paf, rpaf) <= 1e-2
+
+
 def test_body_multiscale_small_frame():
     from pytorch_openpose_b200 import Body
     sd = O.make_weights("body", 1)
