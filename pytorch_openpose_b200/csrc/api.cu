@@ -42,12 +42,34 @@ static ScaleDims scale_dims(int H, int W, double scale) {
     return d;
 }
 
+// Tap tables of one frame plan are laid out in ONE host slab, copied with one stream-ordered transfer into one device
+// allocation; the builders below return slab offsets disguised as pointers, relocated once the device base is known.
+struct TableSlab {
+    std::vector<uint8_t> host;
+    template <typename T>
+    T* add(const std::vector<T>& v) {
+        const size_t off = (host.size() + 15) & ~(size_t)15;
+        host.resize(off + std::max<size_t>(v.size(), 1) * sizeof(T));
+        if (!v.empty()) memcpy(host.data() + off, v.data(), v.size() * sizeof(T));
+        return (T*)off;
+    }
+};
+template <typename T>
+static void relocate(T*& p, uint8_t* base) { p = (T*)(base + (size_t)p); }
+// device copy of a finished slab, ordered on `st` (the slab must outlive the copy)
+static uint8_t* commit_tables(DevPool& pool, const TableSlab& slab, cudaStream_t st) {
+    uint8_t* dev = (uint8_t*)pool.alloc(slab.host.size());
+    OPB_CUDA(cudaMemcpyAsync(dev, slab.host.data(), slab.host.size(), cudaMemcpyHostToDevice, st));
+    return dev;
+}
+
 // fixed-point (11-bit) tap tables of cv2's uint8 cubic resize
 struct U8Taps {
     int *xf, *yf;
     short *xc, *yc;
+    void relocate_to(uint8_t* b) { relocate(xf, b); relocate(yf, b); relocate(xc, b); relocate(yc, b); }
 };
-static U8Taps make_u8_taps(DevPool& pool, int H, int W, const ScaleDims& d) {
+static U8Taps make_u8_taps(TableSlab& pool, int H, int W, const ScaleDims& d) {
     auto conv = [&](const CubicTaps& t, std::vector<short>& out) {
         out.resize(t.coef.size());
         for (size_t i = 0; i < t.coef.size(); ++i) {
@@ -60,10 +82,10 @@ static U8Taps make_u8_taps(DevPool& pool, int H, int W, const ScaleDims& d) {
     conv(tx, sx);
     conv(ty, sy);
     U8Taps u;
-    u.xf = pool.upload(tx.first);
-    u.yf = pool.upload(ty.first);
-    u.xc = pool.upload(sx);
-    u.yc = pool.upload(sy);
+    u.xf = pool.add(tx.first);
+    u.yf = pool.add(ty.first);
+    u.xc = pool.add(sx);
+    u.yc = pool.add(sy);
     return u;
 }
 
@@ -73,17 +95,21 @@ struct UpTables {
     int *ybf, *ybr;       // 16-row strip tables of the register-blocked y pass
     float* ybw;
     int yb_rs;
+    void relocate_to(uint8_t* b) {
+        relocate(xf, b); relocate(yf, b); relocate(xw, b); relocate(yw, b);
+        relocate(ybf, b); relocate(ybr, b); relocate(ybw, b);
+    }
 };
-static UpTables make_up_tables(DevPool& pool, int H, int W, const ScaleDims& d, int n_scales) {
+static UpTables make_up_tables(TableSlab& pool, int H, int W, const ScaleDims& d, int n_scales) {
     std::vector<int> fx, fy;
     std::vector<float> wx, wy;
     composite_taps(d.wo, d.w, W, fx, wx);
     composite_taps(d.ho, d.h, H, fy, wy);
     UpTables t;
-    t.xf = pool.upload(fx);
-    t.yf = pool.upload(fy);
-    t.xw = pool.upload(wx);
-    t.yw = pool.upload(wy);
+    t.xf = pool.add(fx);
+    t.yf = pool.add(fy);
+    t.xw = pool.add(wx);
+    t.yw = pool.add(wy);
     // strips of 16 output rows: first source row, number of source rows, dense weights (x 1/n_scales)
     const int TY = 16, nyb = (H + TY - 1) / TY;
     std::vector<int> bf(nyb), br(nyb);
@@ -105,9 +131,9 @@ static UpTables make_up_tables(DevPool& pool, int H, int W, const ScaleDims& d, 
                 const int r = std::min(fy[y] + k, d.ho - 1) - bf[b];      // same clamp as the generic kernel
                 bw[((size_t)b * rs + r) * TY + (y - b * TY)] += wy[(size_t)y * kUpTaps + k] / (float)n_scales;
             }
-    t.ybf = pool.upload(bf);
-    t.ybr = pool.upload(br);
-    t.ybw = pool.upload(bw);
+    t.ybf = pool.add(bf);
+    t.ybr = pool.add(br);
+    t.ybw = pool.add(bw);
     t.yb_rs = rs;
     return t;
 }
@@ -132,11 +158,14 @@ struct FramePlan {
     std::vector<ScaleDims> dims;
     std::vector<U8Taps> u8taps;
     std::vector<UpTables> uptabs;
-    std::unique_ptr<NetPlan> net;
+    NetPlan* net = nullptr;         // owned by the session's cache: shared by every frame size with the same net input
+    TableSlab tables;               // host copy stays alive until the plan dies (source of an asynchronous copy)
+    // bound from the session's arenas at every submit (one plan is in flight per session)
     uint8_t* d_img = nullptr;
     float* up_scratch = nullptr;
     float* heat_avg = nullptr;      // body: (19,H,W); hand: (n*22,H,W)
     float* paf_avg = nullptr;       // body: (38,H,W)
+    size_t scratch_floats = 0;
     // body post-processing, one set per frame of the batch
     struct BodyPost {
         PeakBuffers pb{};
@@ -211,11 +240,16 @@ struct opb_session {
     int hand_crops = 0;
     Profiler prof;
     cudaEvent_t marks[2] = {nullptr, nullptr};
-    // stage-level net plans (opb_net_forward)
+    // CNN plans keyed by the net input shapes only: every frame / crop size that resizes to the same shapes (all
+    // square hand crops do: 184..736 squared, src/hand.py:38) shares one set of activations and tensor maps
     std::map<std::vector<NetShape>, std::unique_ptr<NetPlan>> net_plans;
+    // size-dependent work buffers, grown to the largest frame seen and shared by all plans of the session
+    enum { AR_IMG, AR_SCRATCH, AR_HEAT, AR_PAF, AR_LABELS, AR_SUMS, AR_PEAKS, AR_COUNT };
+    struct Arena { void* p = nullptr; size_t cap = 0; } arena[AR_COUNT];
     ~opb_session() {
         plans.clear();
         net_plans.clear();
+        for (auto& a : arena) if (a.p) cudaFree(a.p);
         if (host) cudaFreeHost(host);
         if (hand_host) cudaFreeHost(hand_host);
         if (staging) cudaFreeHost(staging);
@@ -248,48 +282,101 @@ static void ensure_staging(opb_session* s, size_t bytes) {
     s->staging_bytes = bytes;
 }
 
+constexpr size_t kMaxFramePlans = 512;     // tap tables only (tens of KB each)
+constexpr size_t kMaxNetPlans = 6;         // activations + tensor maps (hundreds of MB each)
+
+static void drop_plans(opb_session* s, bool nets_too) {
+    OPB_CUDA(cudaStreamSynchronize(s->stream));
+    s->plans.clear();
+    s->active = nullptr;
+    if (nets_too) s->net_plans.clear();
+}
+
+static NetPlan* get_net_plan(opb_session* s, const std::vector<NetShape>& shapes) {
+    auto it = s->net_plans.find(shapes);
+    if (it != s->net_plans.end()) return it->second.get();
+    if (s->net_plans.size() >= kMaxNetPlans) drop_plans(s, true);
+    OPB_CUDA(cudaDeviceSynchronize());          // no other session's work in flight while buffers are created
+    auto plan = build_net_plan(s->net, shapes);
+    // Plan construction uses cudaMalloc / cudaMemset / cudaMemcpy on the legacy default stream, which does NOT order
+    // with the sessions' non-blocking streams: finish it (zero fills included) before any kernel of the plan runs.
+    OPB_CUDA(cudaDeviceSynchronize());
+    NetPlan* raw = plan.get();
+    s->net_plans[shapes] = std::move(plan);
+    return raw;
+}
+
+static void* arena_get(opb_session* s, int which, size_t bytes) {
+    auto& a = s->arena[which];
+    if (a.cap < bytes) {
+        OPB_CUDA(cudaStreamSynchronize(s->stream));
+        if (a.p) OPB_CUDA(cudaFree(a.p));
+        a.p = nullptr;
+        a.cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        OPB_CUDA(cudaMalloc(&a.p, want));
+        a.cap = want;
+    }
+    return a.p;
+}
+
+// points the plan's work buffers at the session's arenas (which may have grown or moved since the last use)
+static void bind_buffers(opb_session* s, FramePlan* fp) {
+    const size_t n = fp->key.n, px = (size_t)fp->key.H * fp->key.W;
+    const bool body = s->net->kind == OPB_NET_BODY;
+    fp->d_img = (uint8_t*)arena_get(s, opb_session::AR_IMG, n * px * 3);
+    fp->up_scratch = (float*)arena_get(s, opb_session::AR_SCRATCH, fp->scratch_floats * sizeof(float));
+    if (body) {
+        fp->heat_avg = (float*)arena_get(s, opb_session::AR_HEAT, n * 19 * px * sizeof(float));
+        fp->paf_avg = (float*)arena_get(s, opb_session::AR_PAF, n * 38 * px * sizeof(float));
+    } else {
+        fp->heat_avg = (float*)arena_get(s, opb_session::AR_HEAT, n * 22 * px * sizeof(float));
+        fp->hb.labels = (int*)arena_get(s, opb_session::AR_LABELS, n * 21 * px * sizeof(int));
+        fp->hb.sums = (double*)arena_get(s, opb_session::AR_SUMS, n * 21 * px * sizeof(double));
+        fp->hb.peaks = (double*)arena_get(s, opb_session::AR_PEAKS, n * 21 * 3 * sizeof(double));
+    }
+}
+
 static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* scales, int n_scales) {
     OPB_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "scale_search must hold 1..8 entries");
     FrameKey key{n, H, W, std::vector<double>(scales, scales + n_scales)};
     auto it = s->plans.find(key);
-    if (it != s->plans.end()) return it->second.get();
+    if (it != s->plans.end()) {
+        bind_buffers(s, it->second.get());
+        return it->second.get();
+    }
     OPB_CUDA(cudaSetDevice(s->net->ctx->device));
-    OPB_CUDA(cudaDeviceSynchronize());          // no other session's work in flight while buffers are created
+    if (s->plans.size() >= kMaxFramePlans) drop_plans(s, false);
     auto fp = std::make_unique<FramePlan>();
     fp->key = key;
     const bool body = s->net->kind == OPB_NET_BODY;
     std::vector<NetShape> shapes;
-    size_t scratch = 0;
     const int C = body ? 57 : 22;
     for (int i = 0; i < n_scales; ++i) {
         const ScaleDims d = scale_dims(H, W, scales[i]);
         fp->dims.push_back(d);
-        fp->u8taps.push_back(make_u8_taps(fp->pool, H, W, d));
-        fp->uptabs.push_back(make_up_tables(fp->pool, H, W, d, n_scales));
+        fp->u8taps.push_back(make_u8_taps(fp->tables, H, W, d));
+        fp->uptabs.push_back(make_up_tables(fp->tables, H, W, d, n_scales));
         shapes.push_back({n, d.hp, d.wp});
-        scratch += (size_t)n * C * d.ho * W;
+        fp->scratch_floats += (size_t)n * C * d.ho * W;
     }
-    fp->net = build_net_plan(s->net, shapes);
-    fp->d_img = fp->pool.alloc_t<uint8_t>((size_t)n * H * W * 3);
-    fp->up_scratch = fp->pool.alloc_t<float>(scratch);
+    fp->net = get_net_plan(s, shapes);          // may drop every cached plan of the session (not this one: not inserted yet)
+    // tables: one device allocation, one copy ordered on the session's stream (no device-wide synchronisation, so a
+    // new crop size on one session does not stall the others)
+    uint8_t* dev_tables = commit_tables(fp->pool, fp->tables, s->stream);
+    for (auto& t : fp->u8taps) t.relocate_to(dev_tables);
+    for (auto& t : fp->uptabs) t.relocate_to(dev_tables);
     fp->launches_per_frame = n_scales /*preprocess*/ + fp->net->kernel_launches;
     if (body) {
-        fp->heat_avg = fp->pool.alloc_t<float>((size_t)n * 19 * H * W);
-        fp->paf_avg = fp->pool.alloc_t<float>((size_t)n * 38 * H * W);
         fp->post.resize(n);
         for (int f = 0; f < n; ++f)
             alloc_body_post(fp->pool, fp->post[f], kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
+        OPB_CUDA(cudaDeviceSynchronize());      // zero fills above ran on the legacy default stream
         fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/);
     } else {
-        fp->heat_avg = fp->pool.alloc_t<float>((size_t)n * 22 * H * W);
-        fp->hb.labels = fp->pool.alloc_t<int>((size_t)n * 21 * H * W);
-        fp->hb.sums = fp->pool.alloc_t<double>((size_t)n * 21 * H * W);
-        fp->hb.peaks = fp->pool.alloc_t<double>((size_t)n * 21 * 3, true);
         fp->launches_per_frame += (n_scales + 1) + 4;
     }
-    // Plan construction uses cudaMalloc / cudaMemset / cudaMemcpy on the legacy default stream, which does NOT order
-    // with the sessions' non-blocking streams: finish it (zero fills included) before any kernel of the plan runs.
-    OPB_CUDA(cudaDeviceSynchronize());
+    bind_buffers(s, fp.get());
     FramePlan* raw = fp.get();
     s->plans[key] = std::move(fp);
     return raw;
@@ -708,7 +795,9 @@ int opb_preprocess(opb_context* ctx, const uint8_t* dev_img, int H, int W, doubl
         OPB_CUDA(cudaSetDevice(ctx->device));
         const ScaleDims d = scale_dims(H, W, scale);
         DevPool pool;
-        const U8Taps t = make_u8_taps(pool, H, W, d);
+        TableSlab slab;
+        U8Taps t = make_u8_taps(slab, H, W, d);
+        t.relocate_to(commit_tables(pool, slab, ctx->stream));
         preprocess_launch(dev_img, H, W, dev_out, d.h, d.w, d.hp, d.wp, t.xf, t.xc, t.yf, t.yc, ctx->stream);
         ctx->launches += 1;
         OPB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -720,11 +809,7 @@ int opb_net_forward(opb_session* s, const uint8_t* dev_in, int n, int hp, int wp
         OPB_REQUIRE(s && dev_in && dev_heat, "null argument");
         OPB_CUDA(cudaSetDevice(s->net->ctx->device));
         std::vector<NetShape> shapes{{n, hp, wp}};
-        auto& plan = s->net_plans[shapes];
-        if (!plan) {
-            plan = build_net_plan(s->net, shapes);
-            OPB_CUDA(cudaDeviceSynchronize());      // zero fills of the plan run on the legacy default stream
-        }
+        NetPlan* plan = get_net_plan(s, shapes);
         const size_t px = (size_t)n * (hp / 8) * (wp / 8);
         OPB_CUDA(cudaMemcpyAsync(plan->in_u8[0], dev_in, (size_t)n * hp * wp * 3, cudaMemcpyDeviceToDevice, s->stream));
         plan->run(s->stream);
@@ -744,13 +829,21 @@ int opb_upsample_avg(opb_context* ctx, const float* const* dev_maps, const doubl
         OPB_REQUIRE(ns >= 1 && ns <= kMaxScales, "1..8 scales");
         OPB_CUDA(cudaSetDevice(ctx->device));
         DevPool pool;
-        UpsampleScale us[kMaxScales];
+        TableSlab slab;
+        std::vector<UpTables> tabs;
+        std::vector<ScaleDims> dims;
         size_t scratch = 0;
         for (int i = 0; i < ns; ++i) {
-            const ScaleDims d = scale_dims(H, W, scales[i]);
-            const UpTables t = make_up_tables(pool, H, W, d, ns);
-            us[i] = UpsampleScale{dev_maps[i], d.ho, d.wo, cstride, t.xf, t.xw, t.yf, t.yw, t.ybf, t.ybr, t.ybw, t.yb_rs};
-            scratch += (size_t)C * d.ho * W;
+            dims.push_back(scale_dims(H, W, scales[i]));
+            tabs.push_back(make_up_tables(slab, H, W, dims[i], ns));
+            scratch += (size_t)C * dims[i].ho * W;
+        }
+        uint8_t* base = commit_tables(pool, slab, ctx->stream);
+        UpsampleScale us[kMaxScales];
+        for (int i = 0; i < ns; ++i) {
+            UpTables& t = tabs[i];
+            t.relocate_to(base);
+            us[i] = UpsampleScale{dev_maps[i], dims[i].ho, dims[i].wo, cstride, t.xf, t.xw, t.yf, t.yw, t.ybf, t.ybr, t.ybw, t.yb_rs};
         }
         float* tmp = pool.alloc_t<float>(scratch);
         upsample_avg_launch2(us, ns, 1, C, H, W, tmp, dev_out, ctx->stream);

@@ -152,6 +152,40 @@ def test_hand_rectangular_crop():
     assert _rel(maps, ravg) <= 2e-2          # Kaiming weights: bf16 through ~50 layers
 
 
+def test_hand_crop_size_changes_every_call():
+    """The real caller's pattern (srcmx/MotionEstimation.py:185-194): the crop width follows the arm, so every call has
+    a new size.  Square crops share one CNN plan (the net input is 184..736 squared for any width) and the session's
+    work buffers; results must not depend on what ran before."""
+    import cv2
+    from pytorch_openpose_b200 import Hand
+    sd = O.make_weights("hand", 5, "kaiming")
+    hand = Hand(sd, scale_search=[0.5, 1.0])
+    rng = np.random.default_rng(9)
+    crops = [cv2.GaussianBlur(rng.integers(0, 256, (w, w, 3), dtype=np.uint8), (0, 0), 2) for w in (150, 201, 97, 150, 64)]
+    first = []
+    for c in crops:
+        peaks = hand(c)
+        maps = hand.last_maps(c.shape)[0]
+        assert np.array_equal(peaks, O.hand_postprocess(maps.astype(np.float64)))
+        first.append(peaks)
+    for c, p in zip(crops, first):                       # revisit: cached plans, buffers grown meanwhile
+        assert np.array_equal(hand(c), p)
+    assert np.array_equal(Hand(sd, scale_search=[0.5, 1.0])(crops[1]), first[1])     # fresh instance agrees
+
+
+def test_hand_many_aspect_ratios_evict_cnn_plans():
+    """More distinct net-input shapes than the session caches (6): plans are dropped and rebuilt, results unchanged."""
+    from pytorch_openpose_b200 import Hand
+    sd = O.make_weights("hand", 1)
+    hand = Hand(sd, scale_search=[1.0])
+    rng = np.random.default_rng(3)
+    crops = [rng.integers(0, 256, (40, 40 + 12 * i, 3), dtype=np.uint8) for i in range(8)]
+    first = [hand(c) for c in crops]
+    again = [hand(c) for c in crops]
+    for a, b in zip(first, again):
+        assert np.array_equal(a, b)
+
+
 def test_synthetic_scene_through_public_api_grouping(golden):
     """The crowded-scene config (BASELINE config 5): 50 people injected at the map boundary -> identical result."""
     from tests import gpu_util as G
