@@ -39,6 +39,15 @@ def smooth_noise_maps(h, w, c, sigma, std, seed):
     return (m / m.std() * std).astype(np.float32).astype(np.float64)
 
 
+def batch_frames(n, h, w, seed):
+    """Deterministic structured float frames in [0,1], NCHW float32 (what transforms.ToTensor yields)."""
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.default_rng(seed)
+    x = np.stack([gaussian_filter(rng.random((3, h, w)), (0, 3, 3)) for _ in range(n)])
+    x = (x - x.min()) / (x.max() - x.min())
+    return x.astype(np.float32)
+
+
 def main():
     import cv2
     import torch
@@ -121,6 +130,28 @@ def main():
     gm = rng.random((40, 33)).astype(np.float32).astype(np.float64)
     np.savez_compressed(os.path.join(OUT, "thirdparty.npz"), versions=v, seed=7, f32_up=up, f32_full=full,
                         gauss=gaussian_filter(gm, sigma=3), **u8, **u8_ipp)
+    # ---- 7. batched estimators (srcmx/Batch_model.py): end to end + their post-processing on injected maps ----
+    RLb = RL.load_batch()
+    out = {}
+    torch.save(sd, os.path.join(tmp, "body.pth"))
+    bb = RLb.Batch_body(os.path.join(tmp, "body.pth"))
+    frames = batch_frames(2, 120, 160, 31)
+    for f, (cand, sub) in enumerate(bb(torch.from_numpy(frames))):
+        out["body_cand_%d" % f], out["body_subset_%d" % f] = np.asarray(cand, dtype=np.float64), sub
+    bh = RLb.Batch_hand(os.path.join(tmp, "hand.pth"))
+    out["hand_peaks"] = bh(torch.from_numpy(batch_frames(2, 96, 96, 32)))
+    bpp, hpp = RL.batch_body_postproc(), RL.batch_hand_postproc()
+    for tag, (H, W, grid) in {"p1": (240, 320, (1, 1)), "p8": (360, 640, (4, 2)), "p50": (720, 1280, (10, 5))}.items():
+        heatm, pafm, _ = O.synthetic_scene(H, W, grid, seed=0)
+        blurred = O.blur5_fixed_order(heatm)
+        (cand, sub), = bpp(bb, torch.from_numpy(blurred.transpose(2, 0, 1)[None].copy()),
+                           pafm.astype(np.float32).transpose(2, 0, 1)[None].copy())
+        out["post_cand_" + tag], out["post_subset_" + tag] = np.asarray(cand, dtype=np.float64), sub
+    hm = O.blur5_fixed_order(smooth_noise_maps(184, 184, 22, 5, 0.03, 21))
+    hm[:, :, 3] = -1.0
+    out["post_hand_peaks"] = hpp(bh, hm[None].copy())
+    np.savez_compressed(os.path.join(OUT, "batch_model.npz"), versions=v, **out)
+
     print("wrote", sorted(os.listdir(OUT)))
     for f in sorted(os.listdir(OUT)):
         print("  %-32s %8d bytes" % (f, os.path.getsize(os.path.join(OUT, f))))

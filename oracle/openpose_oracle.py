@@ -556,6 +556,144 @@ def hand_call(img, sd, scale_search=(0.5, 1.0, 1.5, 2.0), use_cv2=True, bf16=Fal
 
 
 # --------------------------------------------------------------------------------------------
+# batched estimators: Batch_body / Batch_hand, srcmx/Batch_model.py:107-406
+# A second, numerically distinct contract: float frames in [0,1], torch bicubic resizes, one scale,
+# 5x5 blur (utilmx.py:243-263), peaks found AND scored on the blurred map (utilmx.py:230-241).
+# --------------------------------------------------------------------------------------------
+BATCH_BODY_SCALE = 0.5        # Batch_model.py:118
+BATCH_HAND_THRE = 0.035       # Batch_model.py:361
+BLUR5 = np.array([[0.00078633, 0.00655965, 0.01330373, 0.00655965, 0.00078633],       # utilmx.py:248-252
+                  [0.00655965, 0.05472157, 0.11098164, 0.05472157, 0.00655965],
+                  [0.01330373, 0.11098164, 0.22508352, 0.11098164, 0.01330373],
+                  [0.00655965, 0.05472157, 0.11098164, 0.05472157, 0.00655965],
+                  [0.00078633, 0.00655965, 0.01330373, 0.00655965, 0.00078633]], dtype=np.float32)
+
+
+def batch_size_pad(g_scale, height, width):
+    """Batch_body.calculate_size_pad (Batch_model.py:340-345) -> (scale, h, w, pad_h, pad_w)."""
+    scale = BOXSIZE * g_scale / height
+    h, w = int(height * scale), int(width * scale)
+    return scale, h, w, (STRIDE - (h % STRIDE)) % STRIDE, (STRIDE - (w % STRIDE)) % STRIDE
+
+
+def blur5(x):
+    """utilmx.GaussianBlurConv.__call__ (utilmx.py:261-263): depthwise 5x5 on a reflect-padded (no edge repeat)
+    float32 NCHW tensor."""
+    import torch
+    import torch.nn.functional as F
+    c = x.shape[1]
+    w = torch.from_numpy(BLUR5)[None, None].expand(c, 1, 5, 5).contiguous()
+    return F.conv2d(F.pad(x, (2, 2, 2, 2), mode="reflect"), w, groups=c)
+
+
+def blur5_fixed_order(maps):
+    """The same 5x5 blur in a FIXED float32 operation order (taps in row-major order, product and sum rounded
+    separately): what the device kernel computes bit for bit.  torch's depthwise conv adds the same 25 products in an
+    unspecified order, so it agrees with this to a few float32 ulps only.  maps (H,W,C) -> (H,W,C) float32."""
+    m = np.asarray(maps, dtype=np.float32)
+    p = np.pad(m, ((2, 2), (2, 2), (0, 0)), mode="reflect")          # reflect without edge repeat == torch 'reflect'
+    H, W = m.shape[:2]
+    acc = np.zeros_like(m)
+    for dy in range(5):
+        for dx in range(5):
+            acc = acc + BLUR5[dy, dx] * p[dy:dy + H, dx:dx + W]
+    return acc
+
+
+def batch_find_peaks(blurred, thre1=BODY_THRE1):
+    """utilmx.findpeaks_torch (utilmx.py:230-241) + the id/score bookkeeping of Batch_model.py:185-194 for ONE frame.
+    blurred (H,W,>=18) float32.  The threshold comparison happens in float32.  Returns 18 arrays (n,4)."""
+    peaks, counter = [], 0
+    t = np.float32(thre1)
+    for part in range(18):
+        sm = np.asarray(blurred[:, :, part], dtype=np.float32)
+        z = np.zeros_like(sm)
+        nb = [z.copy() for _ in range(4)]
+        nb[0][1:, :] = sm[:-1, :]
+        nb[1][:-1, :] = sm[1:, :]
+        nb[2][:, 1:] = sm[:, :-1]
+        nb[3][:, :-1] = sm[:, 1:]
+        keep = (sm > t) & (sm >= nb[2]) & (sm >= nb[3]) & (sm >= nb[0]) & (sm >= nb[1])
+        ys, xs = np.nonzero(keep)
+        arr = np.zeros((len(xs), 4))
+        arr[:, 0], arr[:, 1], arr[:, 2] = xs, ys, sm[ys, xs]
+        arr[:, 3] = counter + np.arange(len(xs))
+        counter += len(xs)
+        peaks.append(arr)
+    return peaks
+
+
+def batch_body_postprocess(blurred, paf, thre1=BODY_THRE1, thre2=BODY_THRE2):
+    """Peaks + Batch_body.FindBody_frame (Batch_model.py:206-338, the grouping of src/body.py:96-212 with
+    heatmap.shape[0] as the image height) on one frame's maps: blurred (H,W,19) float32, paf (H,W,38) float32."""
+    peaks = batch_find_peaks(blurred, thre1)
+    conns, special = match_limbs(peaks, np.asarray(paf, dtype=np.float64), blurred.shape[0], thre2)
+    return assemble(peaks, conns, special)
+
+
+def batch_body_maps(batch, sd, bf16=False):
+    """Batch_body.__call__ up to the blurred maps (Batch_model.py:142-176).  batch: (B,3,h,w) float32 in [0,1].
+    Returns (blurred heat (B,h,w,19), paf (B,h,w,38)) float32."""
+    import torch
+    import torch.nn.functional as F
+    x = torch.as_tensor(batch, dtype=torch.float32)
+    _, _, h, w = x.shape
+    scale, n_h, n_w, pad_h, pad_w = batch_size_pad(BATCH_BODY_SCALE, h, w)
+    with torch.no_grad():
+        x = F.interpolate(x, scale_factor=scale, mode="bicubic")
+        x = F.pad(x - 0.5, [0, pad_w, 0, pad_h], mode="constant", value=0)
+        paf, heat = body_net(x, sd, bf16)
+        outs = []
+        for m in (heat, paf):
+            m = F.interpolate(torch.as_tensor(m), scale_factor=STRIDE, mode="bicubic")[:, :, :n_h, :n_w]
+            outs.append(F.interpolate(m, size=(h, w), mode="bicubic"))
+        heat = blur5(outs[0])
+    return (np.ascontiguousarray(heat.numpy().transpose(0, 2, 3, 1)),
+            np.ascontiguousarray(outs[1].numpy().transpose(0, 2, 3, 1)))
+
+
+def batch_body_call(batch, sd, bf16=False):
+    """Batch_body.__call__ (Batch_model.py:142-204) -> list of (candidate, subset) per frame."""
+    heat, paf = batch_body_maps(batch, sd, bf16)
+    return [batch_body_postprocess(heat[b], paf[b]) for b in range(len(heat))]
+
+
+def batch_hand_postprocess(blurred, thre=BATCH_HAND_THRE):
+    """Batch_model.py:388-405 for one crop: blurred (h,w,>=21) float32 -> (21,3) float64.  Threshold, component
+    sums (numpy float32 summation) and the maximum all use the blurred map."""
+    from scipy import ndimage as ndi
+    eight = np.ones((3, 3), dtype=int)
+    out = np.zeros((21, 3))
+    for part in range(21):
+        m = np.asarray(blurred[:, :, part], dtype=np.float32)
+        binary = m > np.float32(thre)
+        if not binary.any():
+            continue
+        lab, n = ndi.label(binary, structure=eight)
+        best = int(np.argmax([np.sum(m[lab == i]) for i in range(1, n + 1)])) + 1
+        kept = np.where(lab == best, m, np.float32(0))
+        y, x = divmod(int(np.argmax(kept)), kept.shape[1])
+        out[part] = (x, y, kept[y, x])
+    return out
+
+
+def batch_hand_maps(batch, sd, bf16=False):
+    """Batch_hand.__call__ up to the blurred maps (Batch_model.py:366-386): (B,3,S,S) float32 -> (B,S,S,22)."""
+    import torch
+    import torch.nn.functional as F
+    with torch.no_grad():
+        heat = hand_net(torch.as_tensor(batch, dtype=torch.float32) - 0.5, sd, bf16)
+        heat = blur5(F.interpolate(torch.as_tensor(heat), scale_factor=STRIDE, mode="bicubic"))
+    return np.ascontiguousarray(heat.numpy().transpose(0, 2, 3, 1))
+
+
+def batch_hand_call(batch, sd, bf16=False):
+    """Batch_hand.__call__ (Batch_model.py:366-406) -> (B,21,3) float64."""
+    heat = batch_hand_maps(batch, sd, bf16)
+    return np.array([batch_hand_postprocess(heat[b]) for b in range(len(heat))])
+
+
+# --------------------------------------------------------------------------------------------
 # util.handDetect (src/util.py:133-201)
 # --------------------------------------------------------------------------------------------
 def hand_detect(candidate, subset, img_h, img_w):

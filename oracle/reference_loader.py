@@ -152,3 +152,65 @@ def save_checkpoint(model, path):
     sd = {k.split(".", 1)[1]: v.detach().clone() for k, v in model.state_dict().items()}
     torch.save(sd, path)
     return sd
+
+
+def load_batch():
+    """The reference's batched estimators `Batch_body` / `Batch_hand` (srcmx/Batch_model.py:107-406, SURVEY.md 8f row
+    N2) and `utilmx`.  srcmx imports numba, h5py and tslearn at module top (Batch_model.py:22, utilmx.py:17,26) for code
+    that is not on this path; they are absent here and stubbed."""
+    if "batch" in _cache:
+        return _cache["batch"]
+    load()
+    for name in ("numba", "h5py", "tslearn", "tslearn.metrics"):
+        if name not in sys.modules:
+            try:
+                __import__(name)
+            except Exception:
+                sys.modules[name] = types.ModuleType(name)
+    if not hasattr(sys.modules["numba"], "jit"):
+        sys.modules["numba"].jit = lambda *a, **k: (a[0] if a and callable(a[0]) else (lambda f: f))
+    if not hasattr(sys.modules["tslearn"], "metrics"):
+        sys.modules["tslearn"].metrics = sys.modules["tslearn.metrics"]
+    srcmx = os.path.join(REFERENCE_ROOT, "srcmx")
+    if srcmx not in sys.path:
+        sys.path.insert(0, srcmx)
+    import Batch_model
+    import utilmx
+    ns = types.SimpleNamespace(Batch_body=Batch_model.Batch_body, Batch_hand=Batch_model.Batch_hand, utilmx=utilmx,
+                               module=Batch_model)
+    _cache["batch"] = ns
+    return ns
+
+
+def batch_body_postproc():
+    """The reference's own srcmx/Batch_model.py:173-204 (peak search on the blurred maps, id/score bookkeeping,
+    FindBody_frame per frame) as `f(estimator, blurred_heat (B,19,h,w) torch float32, paf (B,38,h,w) numpy float32)
+    -> [(candidate, subset)]`, so that it can run on injected (device-produced) maps."""
+    if "bbpp" in _cache:
+        return _cache["bbpp"]
+    b = load_batch()
+    path = os.path.join(REFERENCE_ROOT, "srcmx", "Batch_model.py")
+    head, tail = _slice(path, 173, 178), _slice(path, 182, 204)
+    assert head.lstrip().startswith("batch_peaks = utilmx.findpeaks_torch") and tail.rstrip().endswith("return results")
+    src = ("def postproc(self, b_heatmap, b_paf):\n    batch_size = len(b_heatmap)\n"
+           + textwrap.indent(head, "    ") + "\n" + textwrap.indent(tail, "    ") + "\n")
+    g = dict(b.module.__dict__)
+    exec(compile(src, path + ":173-204", "exec"), g)
+    _cache["bbpp"] = g["postproc"]
+    return _cache["bbpp"]
+
+
+def batch_hand_postproc():
+    """srcmx/Batch_model.py:387-406 as `f(estimator, heatmap (B,h,w,22) numpy float32) -> (B,21,3)`; like the
+    reference it zeroes parts of `heatmap` in place (Batch_model.py:400)."""
+    if "bhpp" in _cache:
+        return _cache["bhpp"]
+    b = load_batch()
+    path = os.path.join(REFERENCE_ROOT, "srcmx", "Batch_model.py")
+    body = _slice(path, 387, 406)
+    assert body.lstrip().startswith("Batch_peaks = []") and body.rstrip().endswith("return np.array(Batch_peaks)")
+    src = "def postproc(self, heatmap):\n    batch_size = len(heatmap)\n" + textwrap.indent(body, "    ") + "\n"
+    g = dict(b.module.__dict__)
+    exec(compile(src, path + ":387-406", "exec"), g)
+    _cache["bhpp"] = g["postproc"]
+    return _cache["bhpp"]

@@ -88,3 +88,46 @@ def test_thirdparty_restatements(golden):
     assert np.abs(comp - g["f32_full"]).max() < 1e-5
     gm = rng.random((40, 33)).astype(np.float32).astype(np.float64)
     assert np.array_equal(O.gaussian_sigma3(gm), g["gauss"]), "gaussian must be bit-exact with scipy"
+
+
+# ---- batched estimators (srcmx/Batch_model.py) ------------------------------------------------
+def _flat(c):
+    return np.asarray(c, dtype=np.float64).reshape(-1, 4)
+
+
+def test_batch_body_call_matches_reference(golden):
+    from oracle.make_golden import batch_frames
+    g = golden("batch_model")
+    out = O.batch_body_call(batch_frames(2, 120, 160, 31), O.make_weights("body", 0))
+    for f, (cand, sub) in enumerate(out):
+        assert len(g["body_cand_%d" % f]) > 10
+        assert np.array_equal(_flat(cand), _flat(g["body_cand_%d" % f]))
+        assert np.array_equal(sub, g["body_subset_%d" % f])
+
+
+def test_batch_hand_call_matches_reference(golden):
+    from oracle.make_golden import batch_frames
+    g = golden("batch_model")
+    peaks = O.batch_hand_call(batch_frames(2, 96, 96, 32), O.make_weights("hand", 5, "kaiming"))
+    assert (g["hand_peaks"][:, :, 2] > 0).sum() >= 6
+    assert np.array_equal(peaks, g["hand_peaks"])
+
+
+@pytest.mark.parametrize("tag,H,W,grid", [("p1", 240, 320, (1, 1)), ("p8", 360, 640, (4, 2)),
+                                          ("p50", 720, 1280, (10, 5))])
+def test_batch_body_postproc_scenes(golden, tag, H, W, grid):
+    """Peaks found and scored on the 5x5-blurred map + FindBody_frame, vs the reference's own code on the same maps."""
+    g = golden("batch_model")
+    heat, paf, _ = O.synthetic_scene(H, W, grid, seed=0)
+    cand, sub = O.batch_body_postprocess(O.blur5_fixed_order(heat), paf.astype(np.float32))
+    assert len(sub) >= grid[0] * grid[1]
+    assert np.array_equal(_flat(cand), _flat(g["post_cand_" + tag]))
+    assert np.array_equal(sub, g["post_subset_" + tag])
+
+
+def test_batch_hand_postproc(golden):
+    hm = O.blur5_fixed_order(smooth_noise_maps(184, 184, 22, 5, 0.03, 21))
+    hm[:, :, 3] = -1.0
+    peaks = O.batch_hand_postprocess(hm)
+    assert np.array_equal(peaks, golden("batch_model")["post_hand_peaks"][0])
+    assert np.array_equal(peaks[3], [0, 0, 0]) and (peaks[:, 2] > 0).sum() >= 10

@@ -39,3 +39,28 @@ def test_postproc_live():
     cand, sub = O.body_postprocess(heat, paf, 300)
     assert len(sub_ref) >= 3
     assert np.array_equal(cand, cand_ref) and np.array_equal(sub, sub_ref)
+
+
+def test_batch_estimators_live(tmp_path):
+    """srcmx/Batch_model.py Batch_body / Batch_hand (row N2) run from the reference checkout vs the restatement."""
+    from oracle.make_golden import batch_frames
+    b = RL.load_batch()
+    sd = O.make_weights("body", 3)
+    torch.save(sd, tmp_path / "b.pth")
+    frames = batch_frames(2, 96, 136, 8)
+    ref = b.Batch_body(str(tmp_path / "b.pth"))(torch.from_numpy(frames))
+    for (rc, rs), (mc, ms) in zip(ref, O.batch_body_call(frames, sd)):
+        assert np.array_equal(np.asarray(rc, dtype=np.float64).reshape(-1, 4), mc.reshape(-1, 4)) and np.array_equal(rs, ms)
+    sdh = O.make_weights("hand", 3, "kaiming")
+    torch.save(sdh, tmp_path / "h.pth")
+    crops = batch_frames(2, 64, 64, 9)
+    ref = b.Batch_hand(str(tmp_path / "h.pth"))(torch.from_numpy(crops))
+    assert np.array_equal(ref, O.batch_hand_call(crops, sdh))
+    # the reference's own post-processing on injected maps
+    heat, paf, _ = O.synthetic_scene(300, 400, (3, 1), seed=3)
+    blurred = O.blur5_fixed_order(heat)
+    est = b.Batch_body(str(tmp_path / "b.pth"))
+    (rc, rs), = RL.batch_body_postproc()(est, torch.from_numpy(blurred.transpose(2, 0, 1)[None].copy()),
+                                         paf.astype(np.float32).transpose(2, 0, 1)[None].copy())
+    mc, ms = O.batch_body_postprocess(blurred, paf.astype(np.float32))
+    assert len(rs) == 3 and np.array_equal(np.asarray(rc, dtype=np.float64), mc) and np.array_equal(rs, ms)
