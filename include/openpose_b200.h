@@ -122,6 +122,23 @@ int opb_hand_wait(opb_session* s, double* peaks);
 /* heatmap_avg of the last hand batch: (n_crops, 22, h, w) planar fp32 (src/hand.py:33,57).             */
 int opb_hand_maps(opb_session* s, float* host_heat);
 
+/* ---- batched estimators: srcmx/Batch_model.py (the reference author's throughput path) ---------- */
+/* Batch_body.__call__ (srcmx/Batch_model.py:142-204): `frames` = (n, 3, height, width) float32 planar in
+ * [0,1] (torchvision ToTensor), one scale g_scale (the reference uses 0.5, :118) with truncating sizes
+ * (:340-345), torch bicubic resizes, zero padding after the -0.5 shift, 5x5 blur of the full-size heat
+ * maps (srcmx/utilmx.py:243-263), peaks found and scored on the BLURRED maps (utilmx.py:230-241,
+ * Batch_model.py:194), grouping as Body (Batch_model.py:206-338).  `where`: 0 pageable host, 1 device,
+ * 2 pinned host.  Results: opb_body_wait_batch / opb_body_fetch_frame.                               */
+int opb_batch_body_submit(opb_session* s, const float* frames, int where, int n_frames, int height, int width,
+                          double g_scale);
+/* Batch_hand.__call__ (srcmx/Batch_model.py:366-406): `crops` = (n, 3, height, width) float32 in [0,1],
+ * no resize, x8 bicubic upsampling, 5x5 blur, threshold 0.035 / component sums / maximum all on the
+ * blurred maps.  height and width must be multiples of 8.  Results: opb_hand_wait.                  */
+int opb_batch_hand_submit(opb_session* s, const float* crops, int where, int n_crops, int height, int width);
+/* blurred heat maps of the last batched-estimator call: (n, 19 | 22, height, width) planar fp32; the
+ * un-blurred maps and the PAFs come from opb_body_maps / opb_hand_maps.                             */
+int opb_batch_maps(opb_session* s, float* host_blurred_heat);
+
 /* ---- stage-level entry points on DEVICE buffers (parity tests, per-stage benches) ------------- */
 /* src/body.py:38-41 + src/util.py:12-32: cubic resize by `multiplier`, pad right/bottom with 128 to a
  * multiple of 8.  out_u8: (hp, wp, 3) uint8.  Query the sizes first with opb_scale_dims.             */
@@ -142,6 +159,10 @@ int opb_upsample_avg(opb_context* ctx, const float* const* dev_maps, const doubl
  * reference's order; part_begin: 19 ints.  Returns OPB_ERR_CAPACITY (with *n set) if it overflowed.  */
 int opb_find_peaks(opb_context* ctx, const float* dev_heat, int height, int width, double thre1,
                    double* dev_candidates, int capacity, int* host_part_begin19, int* n);
+/* srcmx/utilmx.py:230-241 + srcmx/Batch_model.py:185-194: peaks of an already blurred planar (>=18, H, W) fp32 map,
+ * threshold compared in float32, scored with the blurred value.  Same outputs as opb_find_peaks.      */
+int opb_find_peaks_blurred(opb_context* ctx, const float* dev_blurred, int height, int width, double thre1,
+                           double* dev_candidates, int capacity, int* host_part_begin19, int* n_candidates);
 /* src/body.py:96-212 on device maps + the candidates of opb_find_peaks.  Results to host.           */
 int opb_group_limbs(opb_context* ctx, const float* dev_paf, int height, int width, const double* dev_candidates,
                     const int* host_part_begin19, double thre2, double* host_subset, int subset_capacity,

@@ -2,6 +2,7 @@
 hand-written sm_100a kernels in libopenpose_b200.so.  See DESIGN.md / INTEGRATION.md."""
 from .body import Body            # noqa: F401
 from .hand import Hand            # noqa: F401
+from .batch_model import Batch_body, Batch_hand      # noqa: F401
 from . import util                # noqa: F401
 
 
@@ -17,3 +18,12 @@ def install_as_src():
     pkg.body, pkg.hand, pkg.util, pkg.model = body, hand, _util, model
     sys.modules.update({"src": pkg, "src.body": body, "src.hand": hand, "src.util": _util, "src.model": model})
     return pkg
+
+
+def install_as_batch_model():
+    """`import Batch_model as BM; BM.Batch_body(path)` (srcmx/Batch_motion_Estimation.py:11,22,60) -> the B200 classes.
+    Only the two estimators are provided; the reference module's video dataset helpers stay where they are."""
+    import sys
+    from . import batch_model
+    sys.modules["Batch_model"] = batch_model
+    return batch_model

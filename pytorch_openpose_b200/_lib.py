@@ -52,12 +52,17 @@ SIGNATURES = {
     "opb_hand_wait": (c_int, [c_void_p, c_void_p]),
     "opb_body_maps": (c_int, [c_void_p, c_void_p, c_void_p]),
     "opb_hand_maps": (c_int, [c_void_p, c_void_p]),
+    "opb_batch_body_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double]),
+    "opb_batch_hand_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int]),
+    "opb_batch_maps": (c_int, [c_void_p, c_void_p]),
     "opb_scale_dims": (c_int, [c_int, c_int, c_double, POINTER(c_int), POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "opb_preprocess": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p]),
     "opb_net_forward": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "opb_upsample_avg": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_double), c_int, c_int, c_int, c_int, c_int,
                                  c_void_p]),
     "opb_find_peaks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_int, POINTER(c_int),
+                               POINTER(c_int)]),
+    "opb_find_peaks_blurred": (c_int, [c_void_p, c_void_p, c_int, c_int, c_double, c_void_p, c_int, POINTER(c_int),
                                POINTER(c_int)]),
     "opb_group_limbs": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, POINTER(c_int), c_double, c_void_p, c_int,
                                 POINTER(c_int), c_void_p, c_int, POINTER(c_int)]),

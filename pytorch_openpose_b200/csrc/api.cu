@@ -89,6 +89,45 @@ static U8Taps make_u8_taps(TableSlab& pool, int H, int W, const ScaleDims& d) {
     return u;
 }
 
+// Batch_body.calculate_size_pad (srcmx/Batch_model.py:340-345): truncating sizes, one scale; Batch_hand: no resize
+static ScaleDims batch_dims(int H, int W, double g_scale, bool body) {
+    OPB_REQUIRE(H > 0 && W > 0, "empty frame");
+    ScaleDims d;
+    if (body) {
+        d.mult = 368.0 * g_scale / (double)H;
+        d.h = (int)((double)H * d.mult);
+        d.w = (int)((double)W * d.mult);
+        OPB_REQUIRE(d.h > 0 && d.w > 0, "scaled frame is empty");
+    } else {
+        OPB_REQUIRE(H % 8 == 0 && W % 8 == 0, "Batch_hand crops must have sides that are multiples of 8 (the reference "
+                                              "upsamples the stride-8 maps by exactly 8, srcmx/Batch_model.py:377)");
+        d.mult = 1.0;
+        d.h = H;
+        d.w = W;
+    }
+    d.hp = (d.h + 7) / 8 * 8;
+    d.wp = (d.w + 7) / 8 * 8;
+    d.ho = d.hp / 8;
+    d.wo = d.wp / 8;
+    return d;
+}
+
+// float tap tables of the torch bicubic resize (batched estimators' front end)
+struct F32Taps {
+    int *xf, *yf;
+    float *xc, *yc;
+    void relocate_to(uint8_t* b) { relocate(xf, b); relocate(yf, b); relocate(xc, b); relocate(yc, b); }
+};
+static F32Taps make_f32_taps(TableSlab& pool, int H, int W, const ScaleDims& d) {
+    const CubicTaps tx = cubic_taps(W, d.w, 1.0 / d.mult), ty = cubic_taps(H, d.h, 1.0 / d.mult);
+    F32Taps u;
+    u.xf = pool.add(tx.first);
+    u.yf = pool.add(ty.first);
+    u.xc = pool.add(tx.coef);
+    u.yc = pool.add(ty.coef);
+    return u;
+}
+
 struct UpTables {
     int *xf, *yf;
     float *xw, *yw;
@@ -144,7 +183,9 @@ static UpTables make_up_tables(TableSlab& pool, int H, int W, const ScaleDims& d
 struct FrameKey {
     int n, H, W;
     std::vector<double> scales;
+    int mode = 0;               // 0: Body / Hand (src/), 1: Batch_body / Batch_hand (srcmx/Batch_model.py)
     bool operator<(const FrameKey& o) const {
+        if (mode != o.mode) return mode < o.mode;
         if (n != o.n) return n < o.n;
         if (H != o.H) return H < o.H;
         if (W != o.W) return W < o.W;
@@ -157,6 +198,7 @@ struct FramePlan {
     FrameKey key;
     std::vector<ScaleDims> dims;
     std::vector<U8Taps> u8taps;
+    std::vector<F32Taps> f32taps;
     std::vector<UpTables> uptabs;
     NetPlan* net = nullptr;         // owned by the session's cache: shared by every frame size with the same net input
     TableSlab tables;               // host copy stays alive until the plan dies (source of an asynchronous copy)
@@ -165,6 +207,7 @@ struct FramePlan {
     float* up_scratch = nullptr;
     float* heat_avg = nullptr;      // body: (19,H,W); hand: (n*22,H,W)
     float* paf_avg = nullptr;       // body: (38,H,W)
+    float* blurred = nullptr;       // batched estimators: 5x5-blurred heat maps, same shape as heat_avg
     size_t scratch_floats = 0;
     // body post-processing, one set per frame of the batch
     struct BodyPost {
@@ -244,7 +287,7 @@ struct opb_session {
     // square hand crops do: 184..736 squared, src/hand.py:38) shares one set of activations and tensor maps
     std::map<std::vector<NetShape>, std::unique_ptr<NetPlan>> net_plans;
     // size-dependent work buffers, grown to the largest frame seen and shared by all plans of the session
-    enum { AR_IMG, AR_SCRATCH, AR_HEAT, AR_PAF, AR_LABELS, AR_SUMS, AR_PEAKS, AR_COUNT };
+    enum { AR_IMG, AR_SCRATCH, AR_HEAT, AR_PAF, AR_LABELS, AR_SUMS, AR_PEAKS, AR_BLUR, AR_COUNT };
     struct Arena { void* p = nullptr; size_t cap = 0; } arena[AR_COUNT];
     ~opb_session() {
         plans.clear();
@@ -324,7 +367,9 @@ static void* arena_get(opb_session* s, int which, size_t bytes) {
 static void bind_buffers(opb_session* s, FramePlan* fp) {
     const size_t n = fp->key.n, px = (size_t)fp->key.H * fp->key.W;
     const bool body = s->net->kind == OPB_NET_BODY;
-    fp->d_img = (uint8_t*)arena_get(s, opb_session::AR_IMG, n * px * 3);
+    const bool batch_mode = fp->key.mode == 1;
+    fp->d_img = (uint8_t*)arena_get(s, opb_session::AR_IMG, n * px * 3 * (batch_mode ? sizeof(float) : 1));
+    if (batch_mode) fp->blurred = (float*)arena_get(s, opb_session::AR_BLUR, n * (body ? 19 : 22) * px * sizeof(float));
     fp->up_scratch = (float*)arena_get(s, opb_session::AR_SCRATCH, fp->scratch_floats * sizeof(float));
     if (body) {
         fp->heat_avg = (float*)arena_get(s, opb_session::AR_HEAT, n * 19 * px * sizeof(float));
@@ -337,9 +382,9 @@ static void bind_buffers(opb_session* s, FramePlan* fp) {
     }
 }
 
-static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* scales, int n_scales) {
+static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* scales, int n_scales, int mode = 0) {
     OPB_REQUIRE(n_scales >= 1 && n_scales <= kMaxScales, "scale_search must hold 1..8 entries");
-    FrameKey key{n, H, W, std::vector<double>(scales, scales + n_scales)};
+    FrameKey key{n, H, W, std::vector<double>(scales, scales + n_scales), mode};
     auto it = s->plans.find(key);
     if (it != s->plans.end()) {
         bind_buffers(s, it->second.get());
@@ -353,11 +398,12 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     std::vector<NetShape> shapes;
     const int C = body ? 57 : 22;
     for (int i = 0; i < n_scales; ++i) {
-        const ScaleDims d = scale_dims(H, W, scales[i]);
+        const ScaleDims d = mode == 1 ? batch_dims(H, W, scales[i], body) : scale_dims(H, W, scales[i]);
         fp->dims.push_back(d);
-        fp->u8taps.push_back(make_u8_taps(fp->tables, H, W, d));
+        if (mode == 1) fp->f32taps.push_back(make_f32_taps(fp->tables, H, W, d));
+        else fp->u8taps.push_back(make_u8_taps(fp->tables, H, W, d));
         fp->uptabs.push_back(make_up_tables(fp->tables, H, W, d, n_scales));
-        shapes.push_back({n, d.hp, d.wp});
+        shapes.push_back({n, d.hp, d.wp, mode == 1 ? 2 : 1});
         fp->scratch_floats += (size_t)n * C * d.ho * W;
     }
     fp->net = get_net_plan(s, shapes);          // may drop every cached plan of the session (not this one: not inserted yet)
@@ -365,6 +411,7 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     // new crop size on one session does not stall the others)
     uint8_t* dev_tables = commit_tables(fp->pool, fp->tables, s->stream);
     for (auto& t : fp->u8taps) t.relocate_to(dev_tables);
+    for (auto& t : fp->f32taps) t.relocate_to(dev_tables);
     for (auto& t : fp->uptabs) t.relocate_to(dev_tables);
     fp->launches_per_frame = n_scales /*preprocess*/ + fp->net->kernel_launches;
     if (body) {
@@ -372,9 +419,9 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
         for (int f = 0; f < n; ++f)
             alloc_body_post(fp->pool, fp->post[f], kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
         OPB_CUDA(cudaDeviceSynchronize());      // zero fills above ran on the legacy default stream
-        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/);
+        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/) + (mode == 1);
     } else {
-        fp->launches_per_frame += (n_scales + 1) + 4;
+        fp->launches_per_frame += (n_scales + 1) + 6 + (mode == 1);
     }
     bind_buffers(s, fp.get());
     FramePlan* raw = fp.get();
@@ -427,27 +474,17 @@ static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int
     upsample_avg_launch2(us, S, n, C, H, W, fp->up_scratch, out, st);
 }
 
-static void body_submit(opb_session* s, const uint8_t* img, int where, int n, int H, int W, const double* scales, int ns) {
-    OPB_REQUIRE(s->net->kind == OPB_NET_BODY, "session was created on a hand network");
-    OPB_REQUIRE(n >= 1 && n <= 64, "1..64 frames per batch");
-    OPB_CUDA(cudaSetDevice(s->net->ctx->device));
-    FramePlan* fp = get_plan(s, n, H, W, scales, ns);
-    ensure_host(s, n, 0);
-    s->active = fp;
-    s->n_frames = n;
+// peaks -> grouping -> result copies for every frame of the batch.  mode 0: sigma-3 smoothing + NMS scored on the raw
+// map (src/body.py:70-94); mode 1: NMS on the 5x5-blurred map scored with the blurred value (utilmx.py:230-241).
+static void body_post_enqueue(opb_session* s, FramePlan* fp, int n, int H, int W) {
     cudaStream_t st = s->stream;
-    s->prof.reset();
-    s->prof.mark(st, "start");
-    upload_image(s, fp, img, where, (size_t)n * H * W * 3);
-    s->prof.mark(st, "h2d");
-    run_front(s, fp, n, H, W);
-    run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
-    run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
-    s->prof.mark(st, "upsample_avg");
     const size_t px = (size_t)H * W;
     for (int f = 0; f < n; ++f) {
         FramePlan::BodyPost& bp = fp->post[f];
-        smooth_nms_launch(fp->heat_avg + f * 19 * px, H, W, 18, 0.1, bp.pb, nullptr, st);          // thre1, src/body.py:30
+        if (fp->key.mode == 1)
+            nms_f32_launch(fp->blurred + f * 19 * px, H, W, 18, 0.1f, bp.pb, st);                  // thre1, Batch_model.py:121
+        else
+            smooth_nms_launch(fp->heat_avg + f * 19 * px, H, W, 18, 0.1, bp.pb, nullptr, st);      // thre1, src/body.py:30
         s->prof.mark(st, "smooth_nms");
         sort_peaks_launch2(bp.pb, 18, bp.part_count, st);
         s->prof.mark(st, "sort_peaks");
@@ -465,6 +502,60 @@ static void body_submit(opb_session* s, const uint8_t* img, int where, int n, in
     }
     OPB_CUDA(cudaEventRecord(s->done, st));
     s->net->ctx->launches += fp->launches_per_frame;
+}
+
+static void body_submit(opb_session* s, const uint8_t* img, int where, int n, int H, int W, const double* scales, int ns) {
+    OPB_REQUIRE(s->net->kind == OPB_NET_BODY, "session was created on a hand network");
+    OPB_REQUIRE(n >= 1 && n <= 64, "1..64 frames per batch");
+    OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+    FramePlan* fp = get_plan(s, n, H, W, scales, ns);
+    ensure_host(s, n, 0);
+    s->active = fp;
+    s->n_frames = n;
+    cudaStream_t st = s->stream;
+    s->prof.reset();
+    s->prof.mark(st, "start");
+    upload_image(s, fp, img, where, (size_t)n * H * W * 3);
+    s->prof.mark(st, "h2d");
+    run_front(s, fp, n, H, W);
+    run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
+    run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
+    s->prof.mark(st, "upsample_avg");
+    body_post_enqueue(s, fp, n, H, W);
+}
+
+// float front end of the batched estimators: resize (body only) - 0.5, zero pad, bf16 HWC3 -> CNN
+static void run_front_f32(opb_session* s, FramePlan* fp, int n, int H, int W) {
+    cudaStream_t st = s->stream;
+    const ScaleDims& d = fp->dims[0];
+    const F32Taps& t = fp->f32taps[0];
+    preprocess_f32_launch((const float*)fp->d_img, n, H, W, fp->net->in_u8[0], d.h, d.w, d.hp, d.wp, t.xf, t.xc, t.yf, t.yc, st);
+    s->prof.mark(st, "preprocess");
+    fp->net->run(st, s->prof.on ? &s->prof : nullptr);
+}
+
+// Batch_body.__call__ (srcmx/Batch_model.py:142-204)
+static void batch_body_submit(opb_session* s, const float* frames, int where, int n, int H, int W, double g_scale) {
+    OPB_REQUIRE(s->net->kind == OPB_NET_BODY, "session was created on a hand network");
+    OPB_REQUIRE(n >= 1 && n <= 64, "1..64 frames per batch");
+    OPB_REQUIRE(g_scale > 0, "scale must be positive");
+    OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+    FramePlan* fp = get_plan(s, n, H, W, &g_scale, 1, 1);
+    ensure_host(s, n, 0);
+    s->active = fp;
+    s->n_frames = n;
+    cudaStream_t st = s->stream;
+    s->prof.reset();
+    s->prof.mark(st, "start");
+    upload_image(s, fp, (const uint8_t*)frames, where, (size_t)n * H * W * 3 * sizeof(float));
+    s->prof.mark(st, "h2d");
+    run_front_f32(s, fp, n, H, W);
+    run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
+    run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
+    s->prof.mark(st, "upsample_avg");
+    blur5_launch(fp->heat_avg, fp->blurred, n * 19, H, W, st);                                     // utilmx.py:261-263
+    s->prof.mark(st, "blur5");
+    body_post_enqueue(s, fp, n, H, W);
 }
 
 // returns the first non-OK per-frame status (OPB_ERR_SUBSET_INDEX mirrors the reference's IndexError)
@@ -542,6 +633,34 @@ static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, in
     run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);
     s->prof.mark(st, "upsample_avg");
     hand_peaks_launch2(fp->heat_avg, n, 22, H, W, 0.03, fp->hb, nullptr, st);        // thre, src/hand.py:31
+    s->prof.mark(st, "hand_peaks");
+    OPB_CUDA(cudaMemcpyAsync(s->hand_host, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    s->prof.mark(st, "d2h");
+    OPB_CUDA(cudaEventRecord(s->done, st));
+    s->net->ctx->launches += fp->launches_per_frame;
+}
+
+// Batch_hand.__call__ (srcmx/Batch_model.py:366-406)
+static void batch_hand_submit(opb_session* s, const float* crops, int where, int n, int H, int W) {
+    OPB_REQUIRE(s->net->kind == OPB_NET_HAND, "session was created on a body network");
+    OPB_REQUIRE(n >= 1 && n <= 1024, "1..1024 crops per batch");
+    OPB_CUDA(cudaSetDevice(s->net->ctx->device));
+    const double one = 1.0;
+    FramePlan* fp = get_plan(s, n, H, W, &one, 1, 1);
+    ensure_host(s, 1, (size_t)n * 63);
+    s->active = fp;
+    s->hand_crops = n;
+    cudaStream_t st = s->stream;
+    s->prof.reset();
+    s->prof.mark(st, "start");
+    upload_image(s, fp, (const uint8_t*)crops, where, (size_t)n * H * W * 3 * sizeof(float));
+    s->prof.mark(st, "h2d");
+    run_front_f32(s, fp, n, H, W);
+    run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);                                    // x8 bicubic, :377
+    s->prof.mark(st, "upsample_avg");
+    blur5_launch(fp->heat_avg, fp->blurred, n * 22, H, W, st);                                     // :378
+    s->prof.mark(st, "blur5");
+    hand_peaks_blurred_launch(fp->blurred, n, 22, H, W, 0.035f, fp->hb, st);                       // thre, :361
     s->prof.mark(st, "hand_peaks");
     OPB_CUDA(cudaMemcpyAsync(s->hand_host, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
     s->prof.mark(st, "d2h");
@@ -763,6 +882,28 @@ int opb_hand_maps(opb_session* s, float* host_heat) {
     });
 }
 
+int opb_batch_body_submit(opb_session* s, const float* frames, int where, int n_frames, int H, int W, double g_scale) {
+    return guarded([&] {
+        OPB_REQUIRE(s && frames, "null argument");
+        batch_body_submit(s, frames, where, n_frames, H, W, g_scale);
+    });
+}
+int opb_batch_hand_submit(opb_session* s, const float* crops, int where, int n, int H, int W) {
+    return guarded([&] {
+        OPB_REQUIRE(s && crops, "null argument");
+        batch_hand_submit(s, crops, where, n, H, W);
+    });
+}
+int opb_batch_maps(opb_session* s, float* host_blurred_heat) {
+    return guarded([&] {
+        OPB_REQUIRE(s && s->active && s->active->key.mode == 1 && host_blurred_heat, "no finished batched-estimator call");
+        OPB_CUDA(cudaEventSynchronize(s->done));
+        const size_t px = (size_t)s->active->key.H * s->active->key.W * s->active->key.n;
+        const int C = s->net->kind == OPB_NET_BODY ? 19 : 22;
+        OPB_CUDA(cudaMemcpy(host_blurred_heat, s->active->blurred, px * C * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
 int opb_hand_submit(opb_session* s, const uint8_t* crops, int img_is_device, int n, int H, int W, const double* scales, int ns) {
     return guarded([&] {
         OPB_REQUIRE(s && crops && scales, "null argument");
@@ -867,6 +1008,33 @@ int opb_find_peaks(opb_context* ctx, const float* dev_heat, int H, int W, double
         pb.part_begin = pool.alloc_t<int>(19, true);
         int* part_count = pool.alloc_t<int>(18, true);
         smooth_nms_launch(dev_heat, H, W, 18, thre1, pb, nullptr, ctx->stream);
+        sort_peaks_launch2(pb, 18, part_count, ctx->stream);
+        ctx->launches += 3;
+        int appended = 0;
+        OPB_CUDA(cudaMemcpyAsync(&appended, pb.count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaMemcpyAsync(host_part_begin19, pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+        *n = appended;
+        if (appended > capacity) throw Error(OPB_ERR_CAPACITY, "peak buffer too small");
+    });
+}
+
+int opb_find_peaks_blurred(opb_context* ctx, const float* dev_blurred, int H, int W, double thre1, double* dev_candidates,
+                           int capacity, int* host_part_begin19, int* n) {
+    return guarded([&] {
+        OPB_REQUIRE(capacity > 0 && dev_candidates && host_part_begin19 && n, "bad arguments");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        DevPool pool;
+        PeakBuffers pb;
+        pb.capacity = capacity;
+        pb.keys = pool.alloc_t<unsigned long long>(capacity);
+        pb.scores = pool.alloc_t<float>(capacity);
+        pb.count = pool.alloc_t<int>(1, true);
+        pb.candidates = dev_candidates;
+        pb.part_begin = pool.alloc_t<int>(19, true);
+        int* part_count = pool.alloc_t<int>(18, true);
+        OPB_CUDA(cudaDeviceSynchronize());
+        nms_f32_launch(dev_blurred, H, W, 18, (float)thre1, pb, ctx->stream);
         sort_peaks_launch2(pb, 18, part_count, ctx->stream);
         ctx->launches += 3;
         int appended = 0;

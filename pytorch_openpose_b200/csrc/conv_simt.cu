@@ -106,14 +106,24 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int kSegPx = 128;                       // pixels per CTA iteration
-constexpr int kRowBytes = (kSegPx + 2) * 3;       // 390 bytes per staged input row
+// input element of conv1_1: uint8 pixels (Body / Hand: x/256 - 0.5 applied here) or bf16 bits (batched estimators,
+// srcmx/Batch_model.py: float frames already resized and shifted by preprocess_f32_kernel)
+__device__ __forceinline__ uint32_t pack_in(uint8_t lo, uint8_t hi) { return pack_norm(lo, hi); }
+__device__ __forceinline__ uint32_t pack_in(uint16_t lo, uint16_t hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+template <typename T> struct InPad;
+template <> struct InPad<uint8_t> { static constexpr uint8_t v = 128; };       // 128/256 - 0.5 == 0: zero padding
+template <> struct InPad<uint16_t> { static constexpr uint16_t v = 0; };
 
-__global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const uint8_t* __restrict__ in, __nv_bfloat16* __restrict__ out,
+constexpr int kSegPx = 128;                       // pixels per CTA iteration
+constexpr int kRowBytes = (kSegPx + 2) * 3;       // 390 elements per staged input row
+
+template <typename T>
+__global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                              const float* __restrict__ w /*[27][64]*/,
                                                              const float* __restrict__ bias, int N, int H, int W,
                                                              int out_cstride, int segs_per_row, int total_segs) {
-    __shared__ uint8_t srow[3][kRowBytes + 2];
+    __shared__ T srow[3][kRowBytes + 2];
+    constexpr T kPad = InPad<T>::v;
     __shared__ uint4 stile[kSegPx * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
@@ -148,12 +158,12 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const uint8_t* _
         bias_r[j][0] = bias[j * 8 + t * 2];
         bias_r[j][1] = bias[j * 8 + t * 2 + 1];
     }
-    const uint8_t* flat = &srow[0][0];
+    const T* flat = &srow[0][0];
 
     // halo bytes of a segment, fetched into registers one iteration ahead so that the global-load latency overlaps
     // the MMAs and stores of the current segment
     constexpr int kPre = (3 * kRowBytes + 127) / 128;          // 10 bytes per thread
-    uint8_t pre[kPre];
+    T pre[kPre];
     auto fetch = [&](int seg) {
         const int sx = seg % segs_per_row;
         const int y = (seg / segs_per_row) % H;
@@ -165,7 +175,7 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const uint8_t* _
             const int r = i / kRowBytes, e = i - r * kRowBytes;
             const int px = e / 3, c = e - px * 3;
             const int yy = y + r - 1, xx = x0 + px - 1;
-            uint8_t v = 128;                                   // 128/256 - 0.5 == 0: zero padding
+            T v = kPad;
             if (i < 3 * kRowBytes && yy >= 0 && yy < H && xx >= 0 && xx < W)
                 v = __ldg(in + ((img * H + yy) * (size_t)W + xx) * 3 + c);
             pre[q] = v;
@@ -198,10 +208,10 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const uint8_t* _
             for (int ks = 0; ks < 2; ++ks) {
                 // a0: (row g, k pair 0), a1: (row g+8, pair 0), a2: (row g, pair +8), a3: (row g+8, pair +8)
                 const int o0 = koff[ks][0], o1 = koff[ks][1], o2 = koff[ks][2], o3 = koff[ks][3];
-                afrag[mt][ks][0] = pack_norm(o0 >= 0 ? flat[p0 + o0] : 128, o1 >= 0 ? flat[p0 + o1] : 128);
-                afrag[mt][ks][1] = pack_norm(o0 >= 0 ? flat[p1 + o0] : 128, o1 >= 0 ? flat[p1 + o1] : 128);
-                afrag[mt][ks][2] = pack_norm(o2 >= 0 ? flat[p0 + o2] : 128, o3 >= 0 ? flat[p0 + o3] : 128);
-                afrag[mt][ks][3] = pack_norm(o2 >= 0 ? flat[p1 + o2] : 128, o3 >= 0 ? flat[p1 + o3] : 128);
+                afrag[mt][ks][0] = pack_in(o0 >= 0 ? flat[p0 + o0] : kPad, o1 >= 0 ? flat[p0 + o1] : kPad);
+                afrag[mt][ks][1] = pack_in(o0 >= 0 ? flat[p1 + o0] : kPad, o1 >= 0 ? flat[p1 + o1] : kPad);
+                afrag[mt][ks][2] = pack_in(o2 >= 0 ? flat[p0 + o2] : kPad, o3 >= 0 ? flat[p0 + o3] : kPad);
+                afrag[mt][ks][3] = pack_in(o2 >= 0 ? flat[p1 + o2] : kPad, o3 >= 0 ? flat[p1 + o3] : kPad);
             }
         }
         uint32_t* st32 = (uint32_t*)stile;
@@ -325,11 +335,12 @@ __global__ void conv_direct_kernel(const __nv_bfloat16* __restrict__ in, const _
 
 void conv_first_launch(const TensorView& in_u8, const TensorView& out, const float* w27x64, const float* bias,
                        cudaStream_t stream) {
-    OPB_REQUIRE(in_u8.elem == 1 && in_u8.c == 3 && in_u8.cstride == 3, "conv_first: input must be dense u8 HWC3");
+    OPB_REQUIRE((in_u8.elem == 1 || in_u8.elem == 2) && in_u8.c == 3 && in_u8.cstride == 3,
+                "conv_first: input must be dense u8 or bf16 HWC3");
     OPB_REQUIRE(out.elem == 2 && out.c == 64 && out.cstride % 8 == 0 && out.coff == 0, "conv_first: output bf16 64ch");
     OPB_REQUIRE(in_u8.w % 4 == 0, "conv_first: padded width must be a multiple of 4");
     static const bool use_simt = getenv("OPB_CONV1_SIMT") != nullptr;      // CUDA-core variant kept for cross-checks
-    if (use_simt) {
+    if (use_simt && in_u8.elem == 1) {
         const size_t total = in_u8.pixels() / 4;               // one thread per 4-pixel strip
         conv_first_kernel<<<(unsigned)((total + 127) / 128), 128, 0, stream>>>(
             (const uint8_t*)in_u8.base, (__nv_bfloat16*)out.base, w27x64, bias, in_u8.n, in_u8.h, in_u8.w, out.cstride);
@@ -338,8 +349,14 @@ void conv_first_launch(const TensorView& in_u8, const TensorView& out, const flo
         const long long total_segs = (long long)segs_per_row * in_u8.h * in_u8.n;
         OPB_REQUIRE(total_segs < (1ll << 31), "conv_first: too many pixels");
         const int grid = (int)std::min<long long>(total_segs, 148 * 16);
-        conv_first_mma_kernel<<<grid, 128, 0, stream>>>((const uint8_t*)in_u8.base, (__nv_bfloat16*)out.base, w27x64, bias,
-                                                       in_u8.n, in_u8.h, in_u8.w, out.cstride, segs_per_row, (int)total_segs);
+        if (in_u8.elem == 1)
+            conv_first_mma_kernel<uint8_t><<<grid, 128, 0, stream>>>((const uint8_t*)in_u8.base, (__nv_bfloat16*)out.base,
+                                                                    w27x64, bias, in_u8.n, in_u8.h, in_u8.w, out.cstride,
+                                                                    segs_per_row, (int)total_segs);
+        else
+            conv_first_mma_kernel<uint16_t><<<grid, 128, 0, stream>>>((const uint16_t*)in_u8.base, (__nv_bfloat16*)out.base,
+                                                                     w27x64, bias, in_u8.n, in_u8.h, in_u8.w, out.cstride,
+                                                                     segs_per_row, (int)total_segs);
     }
     OPB_CUDA(cudaGetLastError());
 }

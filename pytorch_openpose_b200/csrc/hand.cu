@@ -259,7 +259,34 @@ __global__ void __launch_bounds__(1024) hand_select_kernel(const float* __restri
     }
 }
 
+// Batch_hand (srcmx/Batch_model.py:391-392): the map is already blurred; mask = value > thre, compared in float32
+__global__ void hand_mask_kernel(const float* __restrict__ heat, int h, int w, int chan_stride_maps, float thre,
+                                 int* __restrict__ labels) {
+    const int m = blockIdx.z;
+    const int crop = m / 21, part = m - crop * 21;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= w) return;
+    const float v = __ldg(heat + ((size_t)crop * chan_stride_maps + part) * h * w + (size_t)y * w + x);
+    labels[(size_t)m * h * w + (size_t)y * w + x] = v > thre ? y * w + x : -1;
+}
+
 }  // namespace
+
+static void hand_components_launch(const float* heat_planar, int maps, int chan_stride_maps, int h, int w, HandBuffers hb,
+                                   cudaStream_t stream);
+
+// Batch_hand post-processing (srcmx/Batch_model.py:387-406): threshold, component sums and the maximum all on the
+// blurred map that is passed in.
+void hand_peaks_blurred_launch(const float* blurred_planar, int n_crops, int chan_stride_maps, int h, int w, float thre,
+                               HandBuffers hb, cudaStream_t stream) {
+    const int maps = n_crops * 21;
+    OPB_REQUIRE(maps <= 65535, "hand_peaks: too many crops in one batch");
+    OPB_CUDA(cudaMemsetAsync(hb.sums, 0, sizeof(double) * (size_t)maps * h * w, stream));
+    dim3 g(cdiv(w, 128), h, maps);
+    hand_mask_kernel<<<g, 128, 0, stream>>>(blurred_planar, h, w, chan_stride_maps, thre, hb.labels);
+    OPB_CUDA(cudaGetLastError());
+    hand_components_launch(blurred_planar, maps, chan_stride_maps, h, w, hb, stream);
+}
 
 // heat: planar (n_crops * chan_stride_maps, h, w) fp32, the first 21 planes of each crop are used
 void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_maps, int h, int w, double thre,
@@ -271,6 +298,12 @@ void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_m
     hand_smooth_kernel<<<g1, 256, 0, stream>>>(heat_planar, h, w, chan_stride_maps, gauss_taps_sigma3(), thre,
                                                hb.labels, smoothed_out);
     OPB_CUDA(cudaGetLastError());
+    hand_components_launch(heat_planar, maps, chan_stride_maps, h, w, hb, stream);
+}
+
+// labels hold the mask (own raster index or -1): components, per-component sums, selection (src/hand.py:68-74)
+static void hand_components_launch(const float* heat_planar, int maps, int chan_stride_maps, int h, int w, HandBuffers hb,
+                                   cudaStream_t stream) {
     dim3 g2(cdiv(w, 128), h, maps);
     dim3 g0(cdiv(h, 4), maps);
     hand_runs_kernel<<<g0, 128, 0, stream>>>(hb.labels, h, w);

@@ -296,7 +296,8 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
     for (int s = 0; s < S; ++s) {
         const NetShape& sh = shapes[s];
         OPB_REQUIRE(sh.hp % 8 == 0 && sh.wp % 8 == 0 && sh.n >= 1, "padded input dims must be multiples of 8");
-        TensorView in = B.act(sh.n, sh.hp, sh.wp, 3, 1);
+        OPB_REQUIRE(sh.in_elem == 1 || sh.in_elem == 2, "net input is uint8 or bf16");
+        TensorView in = B.act(sh.n, sh.hp, sh.wp, 3, sh.in_elem);
         plan->in_u8.push_back((uint8_t*)in.base);
         TensorView out = B.act(sh.n, sh.hp, sh.wp, 64);
         const DevLayer& d = net->dev.at("conv1_1");

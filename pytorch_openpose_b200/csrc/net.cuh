@@ -73,8 +73,12 @@ struct DevPool {
 // CNN execution plan for a fixed set of input shapes (one entry per scale)
 struct NetShape {
     int n, hp, wp;
+    int in_elem = 1;          // bytes per input element: 1 = uint8 pixels, 2 = bf16 (batched estimators' float frames)
     bool operator<(const NetShape& o) const {
-        return n != o.n ? n < o.n : (hp != o.hp ? hp < o.hp : wp < o.wp);
+        if (n != o.n) return n < o.n;
+        if (hp != o.hp) return hp < o.hp;
+        if (wp != o.wp) return wp < o.wp;
+        return in_elem < o.in_elem;
     }
 };
 // per-step CUDA-event profiler (bench.py roofline numbers; off by default)
@@ -104,7 +108,7 @@ struct Profiler {
 struct NetPlan {
     DevPool pool;
     std::vector<NetShape> shapes;
-    std::vector<uint8_t*> in_u8;                // per scale: (n, hp, wp, 3) uint8 input
+    std::vector<uint8_t*> in_u8;                // per scale: (n, hp, wp, 3) uint8 (or bf16, NetShape::in_elem) input
     std::vector<float*> out_paf, out_heat;      // per scale: fp32 NHWC (cstride 40 / 24); hand: heat only
     std::vector<std::function<void(cudaStream_t)>> steps;
     std::vector<std::string> step_names;        // parallel to steps

@@ -95,6 +95,11 @@ void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t*
                                const int* x_first, const short* x_coef, const int* y_first, const short* y_coef,
                                cudaStream_t stream);
 
+// batched estimators (srcmx/Batch_model.py): float frames -> bf16 HWC3 net input; 5x5 blur of planar maps
+void preprocess_f32_launch(const float* frames, int n, int H, int W, void* out_bf16, int h, int w, int hp, int wp,
+                           const int* x_first, const float* x_w, const int* y_first, const float* y_w, cudaStream_t stream);
+void blur5_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream);
+
 struct UpsampleScale {
     const float* src;         // fp32 NHWC net output
     int ho, wo, cstride;      // source dims and per-pixel stride (elements)
@@ -125,6 +130,7 @@ struct PeakBuffers {
 void smooth_nms_launch(const float* heat_planar, int H, int W, int parts, double thre, PeakBuffers pb,
                        double* smoothed_out /* optional [parts][H][W] or null */, cudaStream_t stream);
 void sort_peaks_launch2(PeakBuffers pb, int parts, int* part_count_scratch, cudaStream_t stream);
+void nms_f32_launch(const float* blurred_planar, int H, int W, int parts, float thre, PeakBuffers pb, cudaStream_t stream);
 
 // ---- PAF grouping (paf.cu)
 struct LimbBuffers {
@@ -151,6 +157,8 @@ struct HandBuffers {
 };
 void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_maps, int h, int w, double thre,
                         HandBuffers hb, double* smoothed_out, cudaStream_t stream);
+void hand_peaks_blurred_launch(const float* blurred_planar, int n_crops, int chan_stride_maps, int h, int w, float thre,
+                               HandBuffers hb, cudaStream_t stream);
 
 // ---- gaussian taps shared by peaks.cu / hand.cu: scipy.ndimage.gaussian_filter(sigma=3) uses
 // radius int(4*3+0.5) = 12 and weights exp(-x^2/18) / sum (src/body.py:75, src/hand.py:62).  The

@@ -187,7 +187,49 @@ __global__ void part_prefix_kernel(const int* __restrict__ part_count, int* __re
     }
 }
 
+// utilmx.findpeaks_torch (utilmx.py:230-241) on an already blurred float32 map: > thre (compared in float32, like torch
+// does for a Python scalar), >= the four zero-padded neighbours; the score is the BLURRED value (Batch_model.py:194).
+__global__ void __launch_bounds__(256) nms_f32_kernel(const float* __restrict__ maps, int H, int W, float thre, PeakBuffers pb) {
+    const int part = blockIdx.z;
+    const float* map = maps + (size_t)part * H * W;
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    bool peak = false;
+    float v = 0.f;
+    if (x < W && y < H) {
+        v = __ldg(map + (size_t)y * W + x);
+        if (v > thre) {
+            const float l = x > 0 ? __ldg(map + (size_t)y * W + x - 1) : 0.f;
+            const float r = x + 1 < W ? __ldg(map + (size_t)y * W + x + 1) : 0.f;
+            const float u = y > 0 ? __ldg(map + (size_t)(y - 1) * W + x) : 0.f;
+            const float d = y + 1 < H ? __ldg(map + (size_t)(y + 1) * W + x) : 0.f;
+            peak = v >= l && v >= r && v >= u && v >= d;
+        }
+    }
+    const unsigned ballot = __ballot_sync(0xffffffffu, peak);
+    if (ballot) {
+        const int lane = threadIdx.x & 31;
+        int base = 0;
+        if (lane == 0) base = atomicAdd(pb.count, __popc(ballot));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (peak) {
+            const int slot = base + __popc(ballot & ((1u << lane) - 1));
+            if (slot < pb.capacity) {
+                pb.keys[slot] = ((unsigned long long)part << 40) | ((unsigned long long)y << 20) | (unsigned)x;
+                pb.scores[slot] = v;
+            }
+        }
+    }
+}
+
 }  // namespace
+
+void nms_f32_launch(const float* blurred_planar, int H, int W, int parts, float thre, PeakBuffers pb, cudaStream_t stream) {
+    OPB_REQUIRE(H < (1 << 20) && W < (1 << 20), "nms: image too large for the key packing");
+    OPB_CUDA(cudaMemsetAsync(pb.count, 0, sizeof(int), stream));
+    dim3 grid(cdiv(W, 32), cdiv(H, 8), parts);
+    nms_f32_kernel<<<grid, 256, 0, stream>>>(blurred_planar, H, W, thre, pb);
+    OPB_CUDA(cudaGetLastError());
+}
 
 void smooth_nms_launch(const float* heat_planar, int H, int W, int parts, double thre, PeakBuffers pb,
                        double* smoothed_out, cudaStream_t stream) {

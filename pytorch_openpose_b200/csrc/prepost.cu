@@ -262,4 +262,109 @@ void upsample_avg_launch2(const UpsampleScale* scales, int n_scales, int n_img, 
     OPB_CUDA(cudaGetLastError());
 }
 
+// ================================================================================================================
+// Batched estimators (srcmx/Batch_model.py Batch_body / Batch_hand)
+// ================================================================================================================
+namespace {
+
+// Front end of Batch_body.__call__ (Batch_model.py:153-155) and Batch_hand.__call__ (:373): float frames in [0,1],
+// planar (n,3,H,W); bicubic resize (torch semantics: A = -0.75, half-pixel centres, clamped taps, no antialias) to
+// (h,w); minus 0.5; zero padding to (hp,wp).  Output: bf16 HWC3, the input format of conv1_1's bf16 variant.  With
+// identical sizes the taps degenerate to (0,1,0,0) and the frame is copied exactly.
+__global__ void __launch_bounds__(128) preprocess_f32_kernel(const float* __restrict__ in, int H, int W,
+                                                             __nv_bfloat16* __restrict__ out, int h, int w, int hp, int wp,
+                                                             const int* __restrict__ xf, const float* __restrict__ xw,
+                                                             const int* __restrict__ yf, const float* __restrict__ yw) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    const size_t img = blockIdx.z;
+    if (x >= wp) return;
+    float r[3] = {0.f, 0.f, 0.f};
+    if (x < w && y < h) {
+        const int x0 = xf[x], y0 = yf[y];
+        float cx[4], cy[4];
+        int xi[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            cx[j] = xw[x * 4 + j];
+            cy[j] = yw[y * 4 + j];
+            xi[j] = min(max(x0 + j, 0), W - 1);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float* plane = in + (img * 3 + c) * (size_t)H * W;
+            float acc = 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float* row = plane + (size_t)min(max(y0 + i, 0), H - 1) * W;
+                float t = __ldg(row + xi[0]) * cx[0];
+#pragma unroll
+                for (int j = 1; j < 4; ++j) t = t + __ldg(row + xi[j]) * cx[j];
+                acc = acc + t * cy[i];
+            }
+            r[c] = acc - 0.5f;
+        }
+    }
+    __nv_bfloat16* o = out + ((img * hp + y) * (size_t)wp + x) * 3;
+    o[0] = __float2bfloat16_rn(r[0]);
+    o[1] = __float2bfloat16_rn(r[1]);
+    o[2] = __float2bfloat16_rn(r[2]);
+}
+
+__device__ __forceinline__ int reflect101(int i, int n) {          // torch 'reflect': no edge repeat
+    if (n == 1) return 0;
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * n - 2 - i;
+    return min(max(i, 0), n - 1);
+}
+
+// utilmx.GaussianBlurConv (utilmx.py:243-263): depthwise 5x5 on a reflect-padded map.  Fixed operation order (taps in
+// row-major order; this file is compiled with --fmad=false so product and sum round separately) == the oracle's
+// blur5_fixed_order bit for bit; torch adds the same 25 products in an unspecified order.
+struct Blur5 { float w[25]; };
+constexpr int BW = 32, BH = 8;
+__global__ void __launch_bounds__(BW * BH) blur5_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
+                                                        const Blur5 k) {
+    __shared__ float tile[BH + 4][BW + 4];
+    const size_t plane = (size_t)blockIdx.z * H * W;
+    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
+    const int tid = threadIdx.y * BW + threadIdx.x;
+    for (int i = tid; i < (BH + 4) * (BW + 4); i += BW * BH) {
+        const int ry = i / (BW + 4), rx = i - ry * (BW + 4);
+        tile[ry][rx] = __ldg(in + plane + (size_t)reflect101(y0 - 2 + ry, H) * W + reflect101(x0 - 2 + rx, W));
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
+    if (x >= W || y >= H) return;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 5; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 5; ++dx) acc = acc + k.w[dy * 5 + dx] * tile[threadIdx.y + dy][threadIdx.x + dx];
+    out[plane + (size_t)y * W + x] = acc;
+}
+
+}  // namespace
+
+void preprocess_f32_launch(const float* frames, int n, int H, int W, void* out_bf16, int h, int w, int hp, int wp,
+                           const int* x_first, const float* x_w, const int* y_first, const float* y_w, cudaStream_t stream) {
+    dim3 grid(cdiv(wp, 128), hp, n);
+    preprocess_f32_kernel<<<grid, 128, 0, stream>>>(frames, H, W, (__nv_bfloat16*)out_bf16, h, w, hp, wp, x_first, x_w,
+                                                    y_first, y_w);
+    OPB_CUDA(cudaGetLastError());
+}
+
+void blur5_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream) {
+    static const float kw[5][5] = {{0.00078633f, 0.00655965f, 0.01330373f, 0.00655965f, 0.00078633f},      // utilmx.py:248-252
+                                   {0.00655965f, 0.05472157f, 0.11098164f, 0.05472157f, 0.00655965f},
+                                   {0.01330373f, 0.11098164f, 0.22508352f, 0.11098164f, 0.01330373f},
+                                   {0.00655965f, 0.05472157f, 0.11098164f, 0.05472157f, 0.00655965f},
+                                   {0.00078633f, 0.00655965f, 0.01330373f, 0.00655965f, 0.00078633f}};
+    Blur5 k;
+    memcpy(k.w, kw, sizeof(k.w));
+    OPB_REQUIRE(n_maps <= 65535, "blur5: too many maps in one launch");
+    dim3 grid(cdiv(W, BW), cdiv(H, BH), n_maps), block(BW, BH);
+    blur5_kernel<<<grid, block, 0, stream>>>(maps_planar, out_planar, H, W, k);
+    OPB_CUDA(cudaGetLastError());
+}
+
 }  // namespace opb

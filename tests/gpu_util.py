@@ -82,6 +82,18 @@ def find_peaks(heat_chw, thre1=0.1, capacity=16384):
     return cand[:n.value].cpu().numpy(), list(pb), cand
 
 
+def find_peaks_blurred(blurred_chw, thre1=0.1, capacity=16384):
+    C, H, W = blurred_chw.shape
+    d = torch.from_numpy(np.ascontiguousarray(blurred_chw, dtype=np.float32)).cuda()
+    cand = torch.zeros((capacity, 4), dtype=torch.float64, device="cuda")
+    pb = (ctypes.c_int * 19)()
+    n = ctypes.c_int()
+    torch.cuda.synchronize()
+    _lib.check(_lib.lib().opb_find_peaks_blurred(ctx(), d.data_ptr(), H, W, thre1, cand.data_ptr(), capacity, pb,
+                                                 ctypes.byref(n)))
+    return cand[:n.value].cpu().numpy(), list(pb), cand
+
+
 def smooth(heat_chw):
     C, H, W = heat_chw.shape
     d = torch.from_numpy(np.ascontiguousarray(heat_chw, dtype=np.float32)).cuda()
