@@ -15,12 +15,23 @@ from .body import _load_checkpoint
 
 
 def _as_float_batch(batch):
-    if hasattr(batch, "detach"):                       # torch tensor (any device)
-        batch = batch.detach().cpu().numpy()
+    """-> (pointer, where, keepalive, shape).  torch CUDA tensors are read in place (where=1), pinned CPU tensors are
+    copied straight from their pages (where=2); anything else goes through the library's pinned staging buffer."""
+    if hasattr(batch, "detach"):
+        t = batch.detach()
+        if t.dim() != 4 or t.shape[1] != 3:
+            raise ValueError("expected a (B, 3, h, w) float batch")
+        import torch
+        if t.is_cuda or t.is_pinned():
+            t = t.to(torch.float32).contiguous()
+            if t.is_cuda:
+                torch.cuda.current_stream(t.device).synchronize()       # producer work is on torch's stream
+            return t.data_ptr(), (1 if t.is_cuda else 2), t, tuple(t.shape)
+        batch = t.numpy()
     arr = np.ascontiguousarray(batch, dtype=np.float32)
     if arr.ndim != 4 or arr.shape[1] != 3:
         raise ValueError("expected a (B, 3, h, w) float batch")
-    return arr
+    return arr.ctypes.data, 0, arr, arr.shape
 
 
 class Batch_body(object):
@@ -34,10 +45,9 @@ class Batch_body(object):
 
     def submit(self, batch_images, session=None):
         s = session or self._session
-        arr = _as_float_batch(batch_images)
-        s._keepalive, s._batch = arr, arr.shape[0]
-        B, _, h, w = arr.shape
-        _lib.check(_lib.lib().opb_batch_body_submit(s.handle, arr.ctypes.data, 0, B, h, w, float(self.scale_search)))
+        ptr, where, s._keepalive, (B, _, h, w) = _as_float_batch(batch_images)
+        s._batch, s._shape = B, (B, h, w)
+        _lib.check(_lib.lib().opb_batch_body_submit(s.handle, ptr, where, B, h, w, float(self.scale_search)))
 
     def collect(self, session=None):
         s = session or self._session
@@ -54,17 +64,16 @@ class Batch_body(object):
         return out
 
     def __call__(self, batch_images):
-        arr = _as_float_batch(batch_images)
         results = []
-        for lo in range(0, len(arr), self.MAX_BATCH):          # activations of 16 frames per launch set
-            self.submit(arr[lo:lo + self.MAX_BATCH])
+        for lo in range(0, len(batch_images), self.MAX_BATCH):          # activations of 16 frames per launch set
+            self.submit(batch_images[lo:lo + self.MAX_BATCH])
             results.extend(self.collect())
         return results
 
     def last_maps(self, session=None):
         """(blurred heat (B,h,w,19), paf (B,h,w,38)) float32 of the last submitted chunk (Batch_model.py:182-183)."""
         s = session or self._session
-        B, _, h, w = s._keepalive.shape
+        B, h, w = s._shape
         blurred = np.empty((B, 19, h, w), dtype=np.float32)
         paf = np.empty((B, 38, h, w), dtype=np.float32)
         _lib.check(_lib.lib().opb_batch_maps(s.handle, blurred.ctypes.data))
@@ -82,13 +91,12 @@ class Batch_hand(object):
 
     def submit(self, batch_imgs, session=None):
         s = session or self._session
-        arr = _as_float_batch(batch_imgs)
-        s._keepalive, s._n = arr, arr.shape[0]
-        B, _, h, w = arr.shape
+        ptr, where, s._keepalive, (B, _, h, w) = _as_float_batch(batch_imgs)
+        s._n, s._shape = B, (B, h, w)
         if h % 8 or w % 8:
             raise ValueError("Batch_hand crops must have sides that are multiples of 8: the reference upsamples the "
                              "stride-8 maps by exactly 8 (srcmx/Batch_model.py:377)")
-        _lib.check(_lib.lib().opb_batch_hand_submit(s.handle, arr.ctypes.data, 0, B, h, w))
+        _lib.check(_lib.lib().opb_batch_hand_submit(s.handle, ptr, where, B, h, w))
 
     def collect(self, session=None):
         s = session or self._session
@@ -97,17 +105,16 @@ class Batch_hand(object):
         return peaks
 
     def __call__(self, batch_imgs):
-        arr = _as_float_batch(batch_imgs)
         out = []
-        for lo in range(0, len(arr), self.MAX_BATCH):
-            self.submit(arr[lo:lo + self.MAX_BATCH])
+        for lo in range(0, len(batch_imgs), self.MAX_BATCH):
+            self.submit(batch_imgs[lo:lo + self.MAX_BATCH])
             out.append(self.collect())
         return np.concatenate(out, 0)
 
     def last_maps(self, session=None):
         """blurred heat maps (B,h,w,22) float32 of the last submitted chunk (Batch_model.py:378-385)."""
         s = session or self._session
-        B, _, h, w = s._keepalive.shape
+        B, h, w = s._shape
         blurred = np.empty((B, 22, h, w), dtype=np.float32)
         _lib.check(_lib.lib().opb_batch_maps(s.handle, blurred.ctypes.data))
         return np.ascontiguousarray(blurred.transpose(0, 2, 3, 1))

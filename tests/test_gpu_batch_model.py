@@ -106,3 +106,18 @@ def test_batch_hand_rejects_sizes_the_reference_cannot_upsample():
     est = Batch_hand(O.make_weights("hand", 0))
     with pytest.raises(ValueError):
         est(np.zeros((1, 3, 100, 100), np.float32))
+
+
+def test_batch_inputs_torch_pinned_and_cuda_tensors():
+    """The reference is fed torch tensors (DataLoader batches, moved with .cuda()); numpy, pinned and CUDA tensors must
+    give the same answer."""
+    import torch
+    from pytorch_openpose_b200 import Batch_body
+    sd = O.make_weights("body", 2, "kaiming")
+    frames = batch_frames(2, 96, 136, 5)
+    est = Batch_body(sd)
+    ref = est(frames)
+    for variant in (torch.from_numpy(frames), torch.from_numpy(frames).pin_memory(), torch.from_numpy(frames).cuda()):
+        out = est(variant)
+        for (c, s), (rc, rs) in zip(out, ref):
+            assert np.array_equal(_flat(c), _flat(rc)) and np.array_equal(s, rs)
