@@ -135,6 +135,12 @@ int opb_batch_body_submit(opb_session* s, const float* frames, int where, int n_
  * no resize, x8 bicubic upsampling, 5x5 blur, threshold 0.035 / component sums / maximum all on the
  * blurred maps.  height and width must be multiples of 8.  Results: opb_hand_wait.                  */
 int opb_batch_hand_submit(opb_session* s, const float* crops, int where, int n_crops, int height, int width);
+/* The same two calls on frames as they come out of the decoder: (n, height, width, 3) uint8; the division by 255
+ * of torchvision's ToTensor (srcmx/Batch_model.py:409, :101-102) is applied on the device, bit-identically, so the
+ * host neither converts nor uploads float pixels.                                                     */
+int opb_batch_body_submit_u8(opb_session* s, const uint8_t* frames_hwc, int where, int n_frames, int height, int width,
+                             double g_scale);
+int opb_batch_hand_submit_u8(opb_session* s, const uint8_t* crops_hwc, int where, int n_crops, int height, int width);
 /* blurred heat maps of the last batched-estimator call: (n, 19 | 22, height, width) planar fp32; the
  * un-blurred maps and the PAFs come from opb_body_maps / opb_hand_maps.                             */
 int opb_batch_maps(opb_session* s, float* host_blurred_heat);

@@ -214,3 +214,29 @@ def batch_hand_postproc():
     exec(compile(src, path + ":387-406", "exec"), g)
     _cache["bhpp"] = g["postproc"]
     return _cache["bhpp"]
+
+
+def load_motion_estimation(body_factory, hand_factory):
+    """srcmx/MotionEstimation.py with its module-level estimator singletons (`Body('../model/...')`, :18-19) built by
+    the given factories instead of from checkpoint files, so that the reference's own extraction job
+    (`Extract_MotionData_from_Video`, :25-77) can run on fake estimators.  Returns the freshly imported module."""
+    ns = load()
+    load_batch()                                   # stubs + srcmx on sys.path
+    import src.body
+    import src.hand
+    keep = (src.body.Body, src.hand.Hand)
+    sys.modules.pop("MotionEstimation", None)
+    src.body.Body, src.hand.Hand = body_factory, hand_factory
+    try:
+        import MotionEstimation
+    finally:
+        src.body.Body, src.hand.Hand = keep
+    assert ns.Hand is keep[1]
+    return MotionEstimation
+
+
+def load_batch_motion_estimation():
+    """srcmx/Batch_motion_Estimation.py (its estimators are module globals assigned by the caller, :22,60)."""
+    load_batch()
+    import Batch_motion_Estimation
+    return Batch_motion_Estimation

@@ -14,6 +14,14 @@ from . import _lib
 from .body import _load_checkpoint
 
 
+def _as_frames_u8(frames, where):
+    """Decoded frames (B, h, w, 3) uint8 as they come out of cv2 -> (pointer, keepalive, (B, h, w))."""
+    arr = np.ascontiguousarray(frames, dtype=np.uint8)
+    if arr.ndim != 4 or arr.shape[3] != 3:
+        raise ValueError("expected (B, h, w, 3) uint8 frames")
+    return arr.ctypes.data, arr, arr.shape[:3]
+
+
 def _as_float_batch(batch):
     """-> (pointer, where, keepalive, shape).  torch CUDA tensors are read in place (where=1), pinned CPU tensors are
     copied straight from their pages (where=2); anything else goes through the library's pinned staging buffer."""
@@ -48,6 +56,14 @@ class Batch_body(object):
         ptr, where, s._keepalive, (B, _, h, w) = _as_float_batch(batch_images)
         s._batch, s._shape = B, (B, h, w)
         _lib.check(_lib.lib().opb_batch_body_submit(s.handle, ptr, where, B, h, w, float(self.scale_search)))
+
+    def submit_frames(self, frames_u8, session=None, where=0):
+        """Same as `submit(ToTensor(frames))` for decoded (B, h, w, 3) uint8 frames, without the host-side float
+        conversion: the division by 255 happens on the device (bit-identical).  where=2: `frames_u8` is pinned."""
+        s = session or self._session
+        ptr, s._keepalive, (B, h, w) = _as_frames_u8(frames_u8, where)
+        s._batch, s._shape = B, (B, h, w)
+        _lib.check(_lib.lib().opb_batch_body_submit_u8(s.handle, ptr, where, B, h, w, float(self.scale_search)))
 
     def collect(self, session=None):
         s = session or self._session
@@ -97,6 +113,15 @@ class Batch_hand(object):
             raise ValueError("Batch_hand crops must have sides that are multiples of 8: the reference upsamples the "
                              "stride-8 maps by exactly 8 (srcmx/Batch_model.py:377)")
         _lib.check(_lib.lib().opb_batch_hand_submit(s.handle, ptr, where, B, h, w))
+
+    def submit_frames(self, crops_u8, session=None, where=0):
+        """`submit(ToTensor(crops))` for (B, h, w, 3) uint8 crops; /255 on the device."""
+        s = session or self._session
+        ptr, s._keepalive, (B, h, w) = _as_frames_u8(crops_u8, where)
+        s._n, s._shape = B, (B, h, w)
+        if h % 8 or w % 8:
+            raise ValueError("Batch_hand crops must have sides that are multiples of 8 (srcmx/Batch_model.py:377)")
+        _lib.check(_lib.lib().opb_batch_hand_submit_u8(s.handle, ptr, where, B, h, w))
 
     def collect(self, session=None):
         s = session or self._session

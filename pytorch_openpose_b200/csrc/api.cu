@@ -183,7 +183,8 @@ static UpTables make_up_tables(TableSlab& pool, int H, int W, const ScaleDims& d
 struct FrameKey {
     int n, H, W;
     std::vector<double> scales;
-    int mode = 0;               // 0: Body / Hand (src/), 1: Batch_body / Batch_hand (srcmx/Batch_model.py)
+    int mode = 0;               // 0: Body / Hand (src/); Batch_body / Batch_hand (srcmx/Batch_model.py): 1 float planar
+                                // frames, 2 decoded uint8 HWC frames (ToTensor's /255 on the device)
     bool operator<(const FrameKey& o) const {
         if (mode != o.mode) return mode < o.mode;
         if (n != o.n) return n < o.n;
@@ -367,8 +368,8 @@ static void* arena_get(opb_session* s, int which, size_t bytes) {
 static void bind_buffers(opb_session* s, FramePlan* fp) {
     const size_t n = fp->key.n, px = (size_t)fp->key.H * fp->key.W;
     const bool body = s->net->kind == OPB_NET_BODY;
-    const bool batch_mode = fp->key.mode == 1;
-    fp->d_img = (uint8_t*)arena_get(s, opb_session::AR_IMG, n * px * 3 * (batch_mode ? sizeof(float) : 1));
+    const bool batch_mode = fp->key.mode >= 1;
+    fp->d_img = (uint8_t*)arena_get(s, opb_session::AR_IMG, n * px * 3 * (fp->key.mode == 1 ? sizeof(float) : 1));
     if (batch_mode) fp->blurred = (float*)arena_get(s, opb_session::AR_BLUR, n * (body ? 19 : 22) * px * sizeof(float));
     fp->up_scratch = (float*)arena_get(s, opb_session::AR_SCRATCH, fp->scratch_floats * sizeof(float));
     if (body) {
@@ -398,12 +399,12 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     std::vector<NetShape> shapes;
     const int C = body ? 57 : 22;
     for (int i = 0; i < n_scales; ++i) {
-        const ScaleDims d = mode == 1 ? batch_dims(H, W, scales[i], body) : scale_dims(H, W, scales[i]);
+        const ScaleDims d = mode >= 1 ? batch_dims(H, W, scales[i], body) : scale_dims(H, W, scales[i]);
         fp->dims.push_back(d);
-        if (mode == 1) fp->f32taps.push_back(make_f32_taps(fp->tables, H, W, d));
+        if (mode >= 1) fp->f32taps.push_back(make_f32_taps(fp->tables, H, W, d));
         else fp->u8taps.push_back(make_u8_taps(fp->tables, H, W, d));
         fp->uptabs.push_back(make_up_tables(fp->tables, H, W, d, n_scales));
-        shapes.push_back({n, d.hp, d.wp, mode == 1 ? 2 : 1});
+        shapes.push_back({n, d.hp, d.wp, mode >= 1 ? 2 : 1});
         fp->scratch_floats += (size_t)n * C * d.ho * W;
     }
     fp->net = get_net_plan(s, shapes);          // may drop every cached plan of the session (not this one: not inserted yet)
@@ -419,9 +420,9 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
         for (int f = 0; f < n; ++f)
             alloc_body_post(fp->pool, fp->post[f], kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
         OPB_CUDA(cudaDeviceSynchronize());      // zero fills above ran on the legacy default stream
-        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/) + (mode == 1);
+        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/) + (mode >= 1);
     } else {
-        fp->launches_per_frame += (n_scales + 1) + 6 + (mode == 1);
+        fp->launches_per_frame += (n_scales + 1) + 6 + (mode >= 1);
     }
     bind_buffers(s, fp.get());
     FramePlan* raw = fp.get();
@@ -481,7 +482,7 @@ static void body_post_enqueue(opb_session* s, FramePlan* fp, int n, int H, int W
     const size_t px = (size_t)H * W;
     for (int f = 0; f < n; ++f) {
         FramePlan::BodyPost& bp = fp->post[f];
-        if (fp->key.mode == 1)
+        if (fp->key.mode >= 1)
             nms_f32_launch(fp->blurred + f * 19 * px, H, W, 18, 0.1f, bp.pb, st);                  // thre1, Batch_model.py:121
         else
             smooth_nms_launch(fp->heat_avg + f * 19 * px, H, W, 18, 0.1, bp.pb, nullptr, st);      // thre1, src/body.py:30
@@ -529,25 +530,25 @@ static void run_front_f32(opb_session* s, FramePlan* fp, int n, int H, int W) {
     cudaStream_t st = s->stream;
     const ScaleDims& d = fp->dims[0];
     const F32Taps& t = fp->f32taps[0];
-    preprocess_f32_launch((const float*)fp->d_img, n, H, W, fp->net->in_u8[0], d.h, d.w, d.hp, d.wp, t.xf, t.xc, t.yf, t.yc, st);
+    preprocess_f32_launch(fp->d_img, fp->key.mode == 2, n, H, W, fp->net->in_u8[0], d.h, d.w, d.hp, d.wp, t.xf, t.xc, t.yf, t.yc, st);
     s->prof.mark(st, "preprocess");
     fp->net->run(st, s->prof.on ? &s->prof : nullptr);
 }
 
 // Batch_body.__call__ (srcmx/Batch_model.py:142-204)
-static void batch_body_submit(opb_session* s, const float* frames, int where, int n, int H, int W, double g_scale) {
+static void batch_body_submit(opb_session* s, const void* frames, bool u8, int where, int n, int H, int W, double g_scale) {
     OPB_REQUIRE(s->net->kind == OPB_NET_BODY, "session was created on a hand network");
     OPB_REQUIRE(n >= 1 && n <= 64, "1..64 frames per batch");
     OPB_REQUIRE(g_scale > 0, "scale must be positive");
     OPB_CUDA(cudaSetDevice(s->net->ctx->device));
-    FramePlan* fp = get_plan(s, n, H, W, &g_scale, 1, 1);
+    FramePlan* fp = get_plan(s, n, H, W, &g_scale, 1, u8 ? 2 : 1);
     ensure_host(s, n, 0);
     s->active = fp;
     s->n_frames = n;
     cudaStream_t st = s->stream;
     s->prof.reset();
     s->prof.mark(st, "start");
-    upload_image(s, fp, (const uint8_t*)frames, where, (size_t)n * H * W * 3 * sizeof(float));
+    upload_image(s, fp, (const uint8_t*)frames, where, (size_t)n * H * W * 3 * (u8 ? 1 : sizeof(float)));
     s->prof.mark(st, "h2d");
     run_front_f32(s, fp, n, H, W);
     run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
@@ -641,19 +642,19 @@ static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, in
 }
 
 // Batch_hand.__call__ (srcmx/Batch_model.py:366-406)
-static void batch_hand_submit(opb_session* s, const float* crops, int where, int n, int H, int W) {
+static void batch_hand_submit(opb_session* s, const void* crops, bool u8, int where, int n, int H, int W) {
     OPB_REQUIRE(s->net->kind == OPB_NET_HAND, "session was created on a body network");
     OPB_REQUIRE(n >= 1 && n <= 1024, "1..1024 crops per batch");
     OPB_CUDA(cudaSetDevice(s->net->ctx->device));
     const double one = 1.0;
-    FramePlan* fp = get_plan(s, n, H, W, &one, 1, 1);
+    FramePlan* fp = get_plan(s, n, H, W, &one, 1, u8 ? 2 : 1);
     ensure_host(s, 1, (size_t)n * 63);
     s->active = fp;
     s->hand_crops = n;
     cudaStream_t st = s->stream;
     s->prof.reset();
     s->prof.mark(st, "start");
-    upload_image(s, fp, (const uint8_t*)crops, where, (size_t)n * H * W * 3 * sizeof(float));
+    upload_image(s, fp, (const uint8_t*)crops, where, (size_t)n * H * W * 3 * (u8 ? 1 : sizeof(float)));
     s->prof.mark(st, "h2d");
     run_front_f32(s, fp, n, H, W);
     run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);                                    // x8 bicubic, :377
@@ -885,18 +886,30 @@ int opb_hand_maps(opb_session* s, float* host_heat) {
 int opb_batch_body_submit(opb_session* s, const float* frames, int where, int n_frames, int H, int W, double g_scale) {
     return guarded([&] {
         OPB_REQUIRE(s && frames, "null argument");
-        batch_body_submit(s, frames, where, n_frames, H, W, g_scale);
+        batch_body_submit(s, frames, false, where, n_frames, H, W, g_scale);
+    });
+}
+int opb_batch_body_submit_u8(opb_session* s, const uint8_t* frames, int where, int n_frames, int H, int W, double g_scale) {
+    return guarded([&] {
+        OPB_REQUIRE(s && frames, "null argument");
+        batch_body_submit(s, frames, true, where, n_frames, H, W, g_scale);
     });
 }
 int opb_batch_hand_submit(opb_session* s, const float* crops, int where, int n, int H, int W) {
     return guarded([&] {
         OPB_REQUIRE(s && crops, "null argument");
-        batch_hand_submit(s, crops, where, n, H, W);
+        batch_hand_submit(s, crops, false, where, n, H, W);
+    });
+}
+int opb_batch_hand_submit_u8(opb_session* s, const uint8_t* crops, int where, int n, int H, int W) {
+    return guarded([&] {
+        OPB_REQUIRE(s && crops, "null argument");
+        batch_hand_submit(s, crops, true, where, n, H, W);
     });
 }
 int opb_batch_maps(opb_session* s, float* host_blurred_heat) {
     return guarded([&] {
-        OPB_REQUIRE(s && s->active && s->active->key.mode == 1 && host_blurred_heat, "no finished batched-estimator call");
+        OPB_REQUIRE(s && s->active && s->active->key.mode >= 1 && host_blurred_heat, "no finished batched-estimator call");
         OPB_CUDA(cudaEventSynchronize(s->done));
         const size_t px = (size_t)s->active->key.H * s->active->key.W * s->active->key.n;
         const int C = s->net->kind == OPB_NET_BODY ? 19 : 22;

@@ -96,8 +96,9 @@ void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t*
                                cudaStream_t stream);
 
 // batched estimators (srcmx/Batch_model.py): float frames -> bf16 HWC3 net input; 5x5 blur of planar maps
-void preprocess_f32_launch(const float* frames, int n, int H, int W, void* out_bf16, int h, int w, int hp, int wp,
-                           const int* x_first, const float* x_w, const int* y_first, const float* y_w, cudaStream_t stream);
+void preprocess_f32_launch(const void* frames, bool frames_u8_hwc, int n, int H, int W, void* out_bf16, int h, int w,
+                           int hp, int wp, const int* x_first, const float* x_w, const int* y_first, const float* y_w,
+                           cudaStream_t stream);
 void blur5_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream);
 
 struct UpsampleScale {

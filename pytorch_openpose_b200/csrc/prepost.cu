@@ -271,7 +271,16 @@ namespace {
 // planar (n,3,H,W); bicubic resize (torch semantics: A = -0.75, half-pixel centres, clamped taps, no antialias) to
 // (h,w); minus 0.5; zero padding to (hp,wp).  Output: bf16 HWC3, the input format of conv1_1's bf16 variant.  With
 // identical sizes the taps degenerate to (0,1,0,0) and the frame is copied exactly.
-__global__ void __launch_bounds__(128) preprocess_f32_kernel(const float* __restrict__ in, int H, int W,
+// sample (c, y, x) of frame `img`: planar float, or decoded uint8 HWC pixels with ToTensor's division by 255 applied here
+__device__ __forceinline__ float frame_at(const float* in, size_t img, int c, int y, int x, int H, int W) {
+    return __ldg(in + ((img * 3 + c) * (size_t)H + y) * W + x);
+}
+__device__ __forceinline__ float frame_at(const uint8_t* in, size_t img, int c, int y, int x, int H, int W) {
+    return (float)__ldg(in + ((img * H + y) * (size_t)W + x) * 3 + c) / 255.0f;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(128) preprocess_f32_kernel(const TIn* __restrict__ in, int H, int W,
                                                              __nv_bfloat16* __restrict__ out, int h, int w, int hp, int wp,
                                                              const int* __restrict__ xf, const float* __restrict__ xw,
                                                              const int* __restrict__ yf, const float* __restrict__ yw) {
@@ -291,14 +300,13 @@ __global__ void __launch_bounds__(128) preprocess_f32_kernel(const float* __rest
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
-            const float* plane = in + (img * 3 + c) * (size_t)H * W;
             float acc = 0.f;
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const float* row = plane + (size_t)min(max(y0 + i, 0), H - 1) * W;
-                float t = __ldg(row + xi[0]) * cx[0];
+                const int yy = min(max(y0 + i, 0), H - 1);
+                float t = frame_at(in, img, c, yy, xi[0], H, W) * cx[0];
 #pragma unroll
-                for (int j = 1; j < 4; ++j) t = t + __ldg(row + xi[j]) * cx[j];
+                for (int j = 1; j < 4; ++j) t = t + frame_at(in, img, c, yy, xi[j], H, W) * cx[j];
                 acc = acc + t * cy[i];
             }
             r[c] = acc - 0.5f;
@@ -345,11 +353,16 @@ __global__ void __launch_bounds__(BW * BH) blur5_kernel(const float* __restrict_
 
 }  // namespace
 
-void preprocess_f32_launch(const float* frames, int n, int H, int W, void* out_bf16, int h, int w, int hp, int wp,
-                           const int* x_first, const float* x_w, const int* y_first, const float* y_w, cudaStream_t stream) {
+void preprocess_f32_launch(const void* frames, bool frames_u8_hwc, int n, int H, int W, void* out_bf16, int h, int w,
+                           int hp, int wp, const int* x_first, const float* x_w, const int* y_first, const float* y_w,
+                           cudaStream_t stream) {
     dim3 grid(cdiv(wp, 128), hp, n);
-    preprocess_f32_kernel<<<grid, 128, 0, stream>>>(frames, H, W, (__nv_bfloat16*)out_bf16, h, w, hp, wp, x_first, x_w,
-                                                    y_first, y_w);
+    if (frames_u8_hwc)
+        preprocess_f32_kernel<uint8_t><<<grid, 128, 0, stream>>>((const uint8_t*)frames, H, W, (__nv_bfloat16*)out_bf16, h, w,
+                                                                 hp, wp, x_first, x_w, y_first, y_w);
+    else
+        preprocess_f32_kernel<float><<<grid, 128, 0, stream>>>((const float*)frames, H, W, (__nv_bfloat16*)out_bf16, h, w, hp,
+                                                               wp, x_first, x_w, y_first, y_w);
     OPB_CUDA(cudaGetLastError());
 }
 

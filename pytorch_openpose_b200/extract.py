@@ -1,0 +1,385 @@
+"""Video -> motion-data files: the extraction jobs around the estimators.
+
+Mirrors, with the same outputs and on-disk formats:
+  * `Extract_MotionData_from_Video`  srcmx/MotionEstimation.py:25-77   -> joblib pkl, float64 (T, 18 | 60, 3)
+  * `Batch_body_extraction`          srcmx/Batch_motion_Estimation.py:66-112   -> joblib pkl, float64 (T, 18, 3)
+  * `Batch_hand_extraction`          srcmx/Batch_motion_Estimation.py:19-63    -> joblib pkl, float64 (T, 42, 3)
+  * `HandImageDataset.__getitem__`   srcmx/Batch_model.py:68-104       (hand crops rebuilt from a saved pose track)
+  * the resume ledger `extract_ed_ing.txt`   srcmx/utilmx.py:190-208
+
+What is different is the plumbing: frames are decoded and ROI-cropped by a background thread into a ring of (pinned)
+batch buffers while the GPU works on the previous batches, and batches go through `Body.submit_batch` on several
+sessions instead of one synchronous call per frame.  The estimators are passed in, so the glue is testable without
+a GPU."""
+import os
+import queue
+import threading
+
+import numpy as np
+
+from . import util
+from .motion import select_person
+
+
+# ---- decode (cv2.VideoCapture, like the reference) ----------------------------------------------------------------
+def frame_count(videopath):
+    import cv2
+    video = cv2.VideoCapture(videopath)
+    if not video.isOpened():
+        return None
+    n = int(video.get(cv2.CAP_PROP_FRAME_COUNT))
+    video.release()
+    return n
+
+
+def _alloc(shape, dtype, pinned):
+    if pinned:
+        import torch
+        t = torch.empty(shape, dtype=getattr(torch, np.dtype(dtype).name), pin_memory=True)
+        return t.numpy(), t
+    return np.empty(shape, dtype=dtype), None
+
+
+class FrameBatches(object):
+    """Iterates over (frames (n, H, W, 3) uint8 BGR view, first_index): ROI-cropped frames of a video in batches,
+    decoded ahead of the consumer into reusable buffers (pinned when `pinned`).  A yielded buffer stays valid until
+    `hold` further batches have been taken.
+
+    workers=1 reads the file front to back like the reference (`video.read()` until it fails) and yields batches in
+    order.  workers=k splits the frame range into k contiguous, batch-aligned segments, one `cv2.VideoCapture` and
+    one thread each (seek with CAP_PROP_POS_FRAMES); batches then arrive in whatever order they are decoded -- every
+    batch carries its first frame index -- and frames past the container's reported count are not read."""
+
+    def __init__(self, videopath, recpoint=None, batch=8, depth=4, pinned=False, workers=1):
+        import cv2
+        probe = cv2.VideoCapture(videopath)
+        if not probe.isOpened():
+            raise FileNotFoundError("the file %s is not exist" % videopath)
+        self.count = int(probe.get(cv2.CAP_PROP_FRAME_COUNT))
+        probe.release()
+        self.videopath, self.recpoint, self.batch, self.pinned = videopath, recpoint, batch, pinned
+        self.hold = max(depth - 2, 1)
+        self.workers = max(1, int(workers))
+        self._q = queue.Queue()
+        n_batches = -(-self.count // batch)
+        per = -(-n_batches // self.workers) * batch
+        self._rings = []
+        for w in range(self.workers):
+            lo = w * per
+            hi = None if self.workers == 1 else min((w + 1) * per, self.count)
+            if self.workers > 1 and lo >= self.count:
+                self._q.put(None)
+                self._rings.append(None)
+                continue
+            ring = {"bufs": None, "free": queue.Queue(), "depth": self.hold + 2}
+            self._rings.append(ring)
+            threading.Thread(target=self._run, args=(w, ring, lo, hi), daemon=True).start()
+
+    def _crop(self, frame):
+        if self.recpoint is None:
+            return frame
+        (x0, y0), (x1, y1) = self.recpoint
+        return frame[y0:y1, x0:x1, :]                 # frame[Recpoint[0][1]:Recpoint[1][1], Recpoint[0][0]:Recpoint[1][0]]
+
+    def _run(self, w, ring, lo, hi):
+        import cv2
+        video = cv2.VideoCapture(self.videopath)
+        try:
+            if lo:
+                video.set(cv2.CAP_PROP_POS_FRAMES, lo)
+            index, cur, fill, first = lo, None, 0, lo
+            while hi is None or index < hi:
+                ret, frame = video.read()
+                if ret is False:
+                    break
+                img = self._crop(frame)
+                if ring["bufs"] is None:
+                    ring["bufs"] = [_alloc((self.batch,) + img.shape, np.uint8, self.pinned) for _ in range(ring["depth"])]
+                    for i in range(ring["depth"]):
+                        ring["free"].put(i)
+                if cur is None:
+                    cur, fill, first = ring["free"].get(), 0, index
+                ring["bufs"][cur][0][fill] = img
+                fill += 1
+                index += 1
+                if fill == self.batch:
+                    self._q.put((w, cur, fill, first))
+                    cur = None
+            if cur is not None and fill:
+                self._q.put((w, cur, fill, first))
+            self._q.put(None)
+        except BaseException as e:                     # surface decode errors in the consumer
+            self._q.put(e)
+        finally:
+            video.release()
+
+    def __iter__(self):
+        held, finished = [], 0
+        while finished < self.workers:
+            item = self._q.get()
+            if item is None:
+                finished += 1
+                continue
+            if isinstance(item, BaseException):
+                raise item
+            w, cur, fill, first = item
+            held.append((w, cur))
+            if len(held) > self.hold:                  # the consumer is done with the oldest buffer
+                ow, oc = held.pop(0)
+                self._rings[ow]["free"].put(oc)
+            yield self._rings[w]["bufs"][cur][0][:fill], first
+
+
+def _job_sessions(estimator, n):
+    """Sessions (stream + plans + buffers) are expensive to warm up: keep them on the estimator across videos."""
+    have = estimator.__dict__.setdefault("_job_sessions", [])
+    while len(have) < n:
+        have.append(estimator.net.session())
+    return have[:n]
+
+
+# ---- per-frame records ----------------------------------------------------------------------------------------------
+def body_pose(candidate, subset):
+    """(18,3) key points of the person with the right-most left shoulder (srcmx/MotionEstimation.py:141-158,
+    srcmx/Batch_motion_Estimation.py:86-105); zeros when nobody was found."""
+    pose = np.zeros((18, 3))
+    chosen = select_person(candidate, subset)
+    if chosen is not None:
+        for k in range(18):
+            idx = int(subset[chosen][k])
+            if idx != -1:
+                pose[k, :] = candidate[idx][:3]
+    return pose, chosen
+
+
+def _hands_into(pose60, frame, candidate, subset, chosen, hand_estimation):
+    """srcmx/MotionEstimation.py:160-194: hands of the chosen person only, left crops mirrored."""
+    for i in range(len(subset)):
+        if i != chosen:
+            subset[i, :] = -1
+    for x, y, w, is_left in util.handDetect(candidate, subset, frame):
+        crop = frame[y:y + w, x:x + w, :]
+        if is_left:
+            peaks = hand_estimation(np.ascontiguousarray(crop[:, ::-1, :]))
+            peaks[:, 0] = np.where(peaks[:, 0] == 0, peaks[:, 0], w - peaks[:, 0] - 1 + x)
+            peaks[:, 1] = np.where(peaks[:, 1] == 0, peaks[:, 1], peaks[:, 1] + y)
+            pose60[18:39, :] = peaks
+        else:
+            peaks = hand_estimation(crop)
+            peaks[:, 0] = np.where(peaks[:, 0] == 0, peaks[:, 0], peaks[:, 0] + x)
+            peaks[:, 1] = np.where(peaks[:, 1] == 0, peaks[:, 1], peaks[:, 1] + y)
+            pose60[39:60, :] = peaks
+
+
+def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, hand_estimation=None, mode="body",
+                              batch=8, sessions=2, pinned=None, log=print, decode_workers=1, stats=None):
+    """`Extract_MotionData_from_Video` (srcmx/MotionEstimation.py:25-77): MotionMat (count, 18 | 60, 3) float64, dumped
+    with joblib to `outpath`.  `body_estimation` is a `Body`: batches of frames are kept in flight on `sessions` of its
+    sessions; any other callable `frame -> (candidate, subset)` is called frame by frame."""
+    import joblib
+    if mode == "bodyhand" and hand_estimation is None:
+        raise ValueError("mode='bodyhand' needs a hand estimator")
+    pipelined = hasattr(body_estimation, "submit_batch")
+    if pinned is None:
+        pinned = pipelined
+    try:
+        src = FrameBatches(videopath, recpoint, batch=batch, depth=sessions + 3, pinned=pinned, workers=decode_workers)
+    except FileNotFoundError as e:
+        log(str(e))
+        return None
+    joints = 60 if mode == "bodyhand" else 18
+    mat = np.zeros((src.count, joints, 3))
+    outname = os.path.split(outpath)[1]
+    done = 0
+
+    def finish(frames, first, results):
+        nonlocal done
+        for f, (candidate, subset) in enumerate(results):
+            if first + f >= len(mat):                                  # container reported fewer frames than it holds
+                break
+            pose, chosen = body_pose(candidate, subset)
+            mat[first + f, :18, :] = pose
+            if mode == "bodyhand" and chosen is not None:
+                _hands_into(mat[first + f], frames[f], candidate, subset, chosen, hand_estimation)
+            if (first + f) % 100 == 0:
+                log("%s-%d/%d" % (outname, first + f, src.count))
+            done += 1
+
+    if pipelined:
+        import time
+        clock = {"decode_wait": 0.0, "submit": 0.0, "collect_wait": 0.0, "records": 0.0}
+        ss = _job_sessions(body_estimation, sessions)
+        pending = []                                                   # (session, frames, first)
+
+        def retire():
+            s, fr, fi = pending.pop(0)
+            t = time.perf_counter()
+            res = body_estimation.collect_batch(s)
+            clock["collect_wait"] += time.perf_counter() - t
+            t = time.perf_counter()
+            finish(fr, fi, res)
+            clock["records"] += time.perf_counter() - t
+
+        it = iter(src)
+        while True:
+            t = time.perf_counter()
+            item = next(it, None)
+            clock["decode_wait"] += time.perf_counter() - t
+            if item is None:
+                break
+            frames, first = item
+            if len(pending) == sessions:
+                retire()
+            s = next(c for c in ss if all(c is not p[0] for p in pending))
+            t = time.perf_counter()
+            body_estimation.submit_batch(frames, s, where=2 if pinned else 0)
+            clock["submit"] += time.perf_counter() - t
+            pending.append((s, frames, first))
+        while pending:
+            retire()
+        if stats is not None:
+            stats.update(clock)
+    else:
+        for frames, first in src:
+            finish(frames, first, [body_estimation(frames[f]) for f in range(len(frames))])
+    joblib.dump(mat, outpath)
+    log("%s is saved!" % outpath)
+    return mat
+
+
+# ---- the batched jobs (srcmx/Batch_motion_Estimation.py) -----------------------------------------------------------
+def to_tensor(frames_u8):
+    """torchvision `transforms.ToTensor()` on a batch: (n,H,W,3) uint8 -> (n,3,H,W) float32 = value / 255."""
+    return np.ascontiguousarray(frames_u8.transpose(0, 3, 1, 2)).astype(np.float32) / np.float32(255)
+
+
+def batch_body_extraction(videopath, outpath, batch_size, recpoint, batch_body_model, log=print, decode_workers=1,
+                          sessions=2):
+    """`Batch_body_extraction` (srcmx/Batch_motion_Estimation.py:66-112) -> MotionMat (COUNTS, 18, 3).  A `Batch_body`
+    of this package is fed the decoded uint8 frames directly (`submit_frames`: ToTensor's /255 on the device) on
+    `sessions` sessions; any other callable gets `ToTensor`-ed float batches like the reference's DataLoader yields."""
+    import joblib
+    pipelined = hasattr(batch_body_model, "submit_frames")
+    try:
+        src = FrameBatches(videopath, recpoint, batch=batch_size, depth=sessions + 3 if pipelined else 4, pinned=pipelined,
+                           workers=decode_workers)
+    except FileNotFoundError as e:
+        log(str(e))
+        return None
+    outname = os.path.split(outpath)[1]
+    mat = np.zeros((src.count, 18, 3))
+    count = 0
+
+    def finish(first, results):
+        nonlocal count
+        for f, (candidate, subset) in enumerate(results):
+            if first + f < len(mat):
+                mat[first + f] = body_pose(candidate, subset)[0]
+            count += 1
+            if count % 1000 == 0:
+                log("%s-%d/%d" % (outname, count, src.count))
+
+    if pipelined:
+        ss = _job_sessions(batch_body_model, sessions)
+        pending = []
+        for frames, first in src:
+            if len(pending) == sessions:
+                s, fi = pending.pop(0)
+                finish(fi, batch_body_model.collect(s))
+            s = next(c for c in ss if all(c is not p[0] for p in pending))
+            batch_body_model.submit_frames(frames, s, where=2)
+            pending.append((s, first))
+        for s, fi in pending:
+            finish(fi, batch_body_model.collect(s))
+    else:
+        for frames, first in src:
+            finish(first, batch_body_model(to_tensor(frames)))
+    joblib.dump(mat, outpath)
+    log("the %s file is saved" % outpath)
+    return mat
+
+
+def hand_crops_from_pose(image, pose, boxsize=368):
+    """`HandImageDataset.__getitem__` (srcmx/Batch_model.py:68-104) for one ROI-cropped frame and its saved (18,3) pose:
+    -> (LeftHand, leftparams, RightHand, rightparams); images uint8 (boxsize, boxsize, 3), grey (128) when the hand
+    is missing, the left one mirrored; params = [x, y, w]."""
+    import cv2
+    subset = np.zeros((1, 20))
+    candidate = np.zeros((20, 4))
+    for i in range(18):
+        subset[0, i] = -1 if sum(pose[i, :]) == 0 else i
+        candidate[i, :2] = pose[i, :2]
+    left = np.zeros((boxsize, boxsize, 3), dtype=np.uint8) + 128
+    right = np.zeros_like(left) + 128
+    leftparams, rightparams = np.zeros((3,)), np.zeros((3,))
+    for x, y, w, is_left in util.handDetect(candidate, subset, image):
+        if not is_left:
+            right = cv2.resize(image[y:y + w, x:x + w, :], (boxsize, boxsize), interpolation=cv2.INTER_CUBIC)
+            rightparams = np.array([x, y, w])
+        else:
+            left = cv2.resize(cv2.flip(image[y:y + w, x:x + w, :], 1), (boxsize, boxsize), interpolation=cv2.INTER_CUBIC)
+            leftparams = np.array([x, y, w])
+    return left, leftparams, right, rightparams
+
+
+def batch_hand_extraction(videopath, motiondata, recpoints, outpath, batch_hand_estimation, boxsize=368, batchsize=32,
+                          log=print):
+    """`Batch_hand_extraction` (srcmx/Batch_motion_Estimation.py:19-63) -> HandMat (COUNTS, 42, 3): rows 0-20 left hand,
+    21-41 right hand, in ROI coordinates; a coordinate of exactly 0 means "missing" and is not offset."""
+    import joblib
+    src = FrameBatches(videopath, recpoints, batch=batchsize, depth=4, pinned=False)
+    assert src.count == len(motiondata)
+    mat = np.zeros((len(motiondata), 42, 3))
+    count = 0
+    for frames, first in src:
+        items = [hand_crops_from_pose(frames[f], motiondata[first + f], boxsize) for f in range(len(frames))]
+        lefts = batch_hand_estimation(to_tensor(np.stack([it[0] for it in items])))
+        rights = batch_hand_estimation(to_tensor(np.stack([it[2] for it in items])))
+        for i, (_, (lx, ly, lw), _, (rx, ry, rw)) in enumerate(items):
+            rpeaks = rights[i]
+            rpeaks[:, :2] = rpeaks[:, :2] * rw / boxsize
+            rpeaks[:, 0] = np.where(rpeaks[:, 0] == 0, rpeaks[:, 0], rpeaks[:, 0] + rx)
+            rpeaks[:, 1] = np.where(rpeaks[:, 1] == 0, rpeaks[:, 1], rpeaks[:, 1] + ry)
+            mat[count, 21:, :] = rpeaks
+            lpeaks = lefts[i]
+            lpeaks[:, :2] = lpeaks[:, :2] * lw / boxsize
+            lpeaks[:, 0] = np.where(lpeaks[:, 0] == 0, lpeaks[:, 0], lw - lpeaks[:, 0] - 1 + lx)
+            lpeaks[:, 1] = np.where(lpeaks[:, 1] == 0, lpeaks[:, 1], lpeaks[:, 1] + ly)
+            mat[count, :21, :] = lpeaks
+            count += 1
+            if count % 1000 == 0:
+                log("%s-%d/%d" % (outpath, count, len(motiondata)))
+    joblib.dump(mat, outpath)
+    log("the %s file is saved" % outpath)
+    return mat
+
+
+# ---- resume ledger (srcmx/utilmx.py:190-208) ----------------------------------------------------------------------
+class ExtractLedger(object):
+    """`extract_ed_ing.txt` in the data directory: one output file name per line, appended BEFORE a video is processed
+    so that several workers (one per GPU) sharing the directory skip each other's videos."""
+    NAME = "extract_ed_ing.txt"
+
+    def __init__(self, datadir):
+        self.path = os.path.join(datadir, self.NAME)
+        self.datadir = datadir
+
+    def files(self, init=False):
+        """init=True rebuilds the ledger from the .npy / .pkl files present; entries keep their trailing newline when
+        read back, exactly like the reference's readlines()."""
+        if init:
+            names = [f for f in os.listdir(self.datadir) if os.path.splitext(f)[1] in (".npy", ".pkl")]
+            with open(self.path, "w") as f:
+                for name in names:
+                    f.write("%s\n" % name)
+            return names
+        with open(self.path, "r") as f:
+            return f.readlines()
+
+    def add(self, name):
+        with open(self.path, "a") as f:
+            f.write("%s\n" % name)
+
+    def claimed(self, outname):
+        """The reference's test: the first 9 characters ('video-XXX') of any ledger line (Batch_motion_Estimation.py:156)."""
+        return outname[:9] in [x[:9] for x in self.files()]

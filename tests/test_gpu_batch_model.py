@@ -121,3 +121,25 @@ def test_batch_inputs_torch_pinned_and_cuda_tensors():
         out = est(variant)
         for (c, s), (rc, rs) in zip(out, ref):
             assert np.array_equal(_flat(c), _flat(rc)) and np.array_equal(s, rs)
+
+
+def test_uint8_frames_equal_totensor_floats():
+    """submit_frames (decoded uint8 frames, /255 on the device) == submit(ToTensor(frames)), bit for bit."""
+    from pytorch_openpose_b200 import Batch_body, Batch_hand, extract
+    rng = np.random.default_rng(3)
+    import cv2
+    frames = np.stack([cv2.GaussianBlur(rng.integers(0, 256, (120, 160, 3), dtype=np.uint8), (0, 0), 3) for _ in range(2)])
+    est = Batch_body(O.make_weights("body", 2, "kaiming"))
+    ref = est(extract.to_tensor(frames))
+    ref_maps = est.last_maps()
+    est.submit_frames(frames)
+    out = est.collect()
+    maps = est.last_maps()
+    assert np.array_equal(maps[0], ref_maps[0]) and np.array_equal(maps[1], ref_maps[1])
+    for (c, s), (rc, rs) in zip(out, ref):
+        assert np.array_equal(_flat(c), _flat(rc)) and np.array_equal(s, rs)
+    crops = frames[:, :96, :96]
+    hest = Batch_hand(O.make_weights("hand", 5, "kaiming"))
+    href = hest(extract.to_tensor(crops))
+    hest.submit_frames(crops)
+    assert np.array_equal(hest.collect(), href)
