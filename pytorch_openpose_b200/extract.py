@@ -383,3 +383,27 @@ class ExtractLedger(object):
     def claimed(self, outname):
         """The reference's test: the first 9 characters ('video-XXX') of any ledger line (Batch_motion_Estimation.py:156)."""
         return outname[:9] in [x[:9] for x in self.files()]
+
+
+# ---- combined dictionary (srcmx/MotionEstimation.py:307-341) ---------------------------------------------------------
+def combine_motion_data(datafolder, outpath, mode, pattern=r"\d+"):
+    """`CombineMotiondata`: every .npy / .pkl track in `datafolder` under the first number in its file name ->
+    {key: (positions int16 (T,18,2), scores float32 (T,18))}, dumped with joblib.  Like the reference, mode
+    'bodyhand' converts the tracks but stores nothing (the assignment is missing at MotionEstimation.py:336-340), so
+    its dictionary is empty; files whose key was already taken are skipped in os.listdir order."""
+    import re
+    import joblib
+    out = {}
+    for filename in os.listdir(datafolder):
+        ext = os.path.splitext(filename)[1]
+        key = re.findall(pattern, filename)
+        if len(key) == 0 or key[0] in out:
+            continue
+        if ext not in (".npy", ".pkl"):
+            continue
+        path = os.path.join(datafolder, filename)
+        data = np.load(path) if ext == ".npy" else joblib.load(path)
+        if mode == "body":
+            out[key[0]] = (data[:, :18, :2].astype(np.int16), data[:, :18, -1].astype(np.float32))
+    joblib.dump(out, outpath)
+    return out

@@ -189,3 +189,25 @@ def test_batch_jobs_match_reference_jobs(video, tmp_path):
     from torchvision import transforms
     fr = np.random.default_rng(1).integers(0, 256, (2, 9, 11, 3), dtype=np.uint8)
     assert np.array_equal(E.to_tensor(fr)[1], transforms.ToTensor()(fr[1]).numpy())
+
+
+@live
+def test_combined_dictionary_matches_reference(tmp_path):
+    import joblib
+    ME = RL.load_motion_estimation(lambda path: fake_body, lambda path: fake_hand)
+    d = tmp_path / "data"
+    d.mkdir()
+    rng = np.random.default_rng(5)
+    joblib.dump(rng.random((7, 18, 3)) * 300, str(d / "video-012-body.pkl"))
+    joblib.dump(rng.random((5, 60, 3)) * 300, str(d / "video-034-bodyhand.pkl"))
+    np.save(str(d / "video-056-body.npy"), rng.random((4, 18, 3)) * 300)
+    (d / "readme.txt").write_text("x")
+    for mode in ("body", "bodyhand"):
+        ME.CombineMotiondata(str(d), str(tmp_path / "ref.pkl"), mode)
+        mine = E.combine_motion_data(str(d), str(tmp_path / "mine.pkl"), mode)
+        ref = joblib.load(str(tmp_path / "ref.pkl"))
+        assert sorted(ref) == sorted(mine) == sorted(joblib.load(str(tmp_path / "mine.pkl")))
+        for k in ref:
+            assert ref[k][0].dtype == mine[k][0].dtype == np.int16 and ref[k][1].dtype == mine[k][1].dtype == np.float32
+            assert np.array_equal(ref[k][0], mine[k][0]) and np.array_equal(ref[k][1], mine[k][1])
+    assert len(ref) == 0                           # the reference's bodyhand branch never stores anything
