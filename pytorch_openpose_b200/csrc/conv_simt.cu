@@ -106,29 +106,44 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// input element of conv1_1: uint8 pixels (Body / Hand: x/256 - 0.5 applied here) or bf16 bits (batched estimators,
-// srcmx/Batch_model.py: float frames already resized and shifted by preprocess_f32_kernel)
-__device__ __forceinline__ uint32_t pack_in(uint8_t lo, uint8_t hi) { return pack_norm(lo, hi); }
-__device__ __forceinline__ uint32_t pack_in(uint16_t lo, uint16_t hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
-template <typename T> struct InPad;
-template <> struct InPad<uint8_t> { static constexpr uint8_t v = 128; };       // 128/256 - 0.5 == 0: zero padding
-template <> struct InPad<uint16_t> { static constexpr uint16_t v = 0; };
-
+// input element of conv1_1: uint8 pixels (Body / Hand: x/256 - 0.5 applied while staging, exact in bf16) or bf16 bits
+// (batched estimators, srcmx/Batch_model.py: float frames already resized and shifted by preprocess_f32_kernel)
 constexpr int kSegPx = 128;                       // pixels per CTA iteration
-constexpr int kRowBytes = (kSegPx + 2) * 3;       // 390 elements per staged input row
+constexpr int kRowElems = 392;                    // staged halo row: 1 lead element + 130 pixels x 3 + 1 tail (word aligned)
+constexpr int kRowPitch = 400;                    // smem pitch in bf16 elements
+
+template <typename T> struct InWord;              // one aligned 32-bit global load = kPer input elements
+template <> struct InWord<uint8_t> { static constexpr int kPer = 4; };
+template <> struct InWord<uint16_t> { static constexpr int kPer = 2; };
+
+__device__ __forceinline__ void stage_word(uint16_t* dst, uint32_t word, bool valid, uint8_t) {
+    // 4 pixels bytes -> 4 bf16 of (v/256 - 0.5); outside the image: 0 (the convolution's zero padding)
+    uint2 o = make_uint2(0u, 0u);
+    if (valid) {
+        o.x = pack_norm((uint8_t)(word & 0xff), (uint8_t)((word >> 8) & 0xff));
+        o.y = pack_norm((uint8_t)((word >> 16) & 0xff), (uint8_t)(word >> 24));
+    }
+    *(uint2*)dst = o;
+}
+__device__ __forceinline__ void stage_word(uint16_t* dst, uint32_t word, bool valid, uint16_t) {
+    *(uint32_t*)dst = valid ? word : 0u;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
                                                              const float* __restrict__ w /*[27][64]*/,
                                                              const float* __restrict__ bias, int N, int H, int W,
                                                              int out_cstride, int segs_per_row, int total_segs) {
-    __shared__ T srow[3][kRowBytes + 2];
-    constexpr T kPad = InPad<T>::v;
+    constexpr int kPer = InWord<T>::kPer;
+    constexpr int kWordsPerRow = kRowElems / kPer;                  // 98 (uint8) or 196 (bf16)
+    constexpr int kLoadsPerRow = (kWordsPerRow + 127) / 128;        // 1 or 2 per thread and row
+    __shared__ __align__(16) uint16_t srow[3][kRowPitch];
     __shared__ uint4 stile[kSegPx * 8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int g = lane >> 2, t = lane & 3;
 
-    // per-lane k offsets inside the staged halo: k -> (dy, dx, c); k >= 27 reads a dedicated pad byte (value 128)
+    // per-lane k offsets inside the staged halo: k -> (dy, dx, c); element (pixel p, channel c) of halo row dy sits at
+    // dy * kRowPitch + 1 + p * 3 + c (the row is staged from one element before pixel -1 so that loads are aligned)
     int koff[2][4];
 #pragma unroll
     for (int ks = 0; ks < 2; ++ks)
@@ -136,7 +151,7 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
         for (int q = 0; q < 4; ++q) {
             const int k = ks * 16 + t * 2 + (q & 1) + (q >> 1) * 8;
             const int tap = k / 3, c = k - tap * 3;
-            koff[ks][q] = k < 27 ? (tap / 3) * (kRowBytes + 2) + (tap % 3) * 3 + c : -1;
+            koff[ks][q] = k < 27 ? (tap / 3) * kRowPitch + (tap % 3) * 3 + c + 1 : -1;
         }
     // B fragments: b[j][ks][0] = (W[kb+2t][n], W[kb+2t+1][n]), b[j][ks][1] = (W[kb+2t+8][n], W[kb+2t+9][n]), n = 8j+g
     uint32_t bfrag[8][2][2];
@@ -158,27 +173,32 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
         bias_r[j][0] = bias[j * 8 + t * 2];
         bias_r[j][1] = bias[j * 8 + t * 2 + 1];
     }
-    const T* flat = &srow[0][0];
+    const uint16_t* flat = &srow[0][0];
 
-    // halo bytes of a segment, fetched into registers one iteration ahead so that the global-load latency overlaps
-    // the MMAs and stores of the current segment
-    constexpr int kPre = (3 * kRowBytes + 127) / 128;          // 10 bytes per thread
-    T pre[kPre];
+    // The halo of a segment = 3 image rows x 392 consecutive elements starting at flat element (x0 - 1) * 3 - 1 of the
+    // row, which is 4-byte aligned for both element types (W % 4 == 0): fetched as whole 32-bit words, one iteration
+    // ahead, so that the global-load latency overlaps the MMAs and stores of the current segment.  A word lies either
+    // completely inside the image row or completely outside (then it stages zeros: the padding).
+    uint32_t pre[3][kLoadsPerRow];
+    unsigned pre_valid = 0;
     auto fetch = [&](int seg) {
         const int sx = seg % segs_per_row;
         const int y = (seg / segs_per_row) % H;
         const size_t img = seg / (segs_per_row * H);
-        const int x0 = sx * kSegPx;
+        const int first = (sx * kSegPx - 1) * 3 - 1;                 // flat element index of staged element 0
+        pre_valid = 0;
 #pragma unroll
-        for (int q = 0; q < kPre; ++q) {
-            const int i = threadIdx.x + q * 128;
-            const int r = i / kRowBytes, e = i - r * kRowBytes;
-            const int px = e / 3, c = e - px * 3;
-            const int yy = y + r - 1, xx = x0 + px - 1;
-            T v = kPad;
-            if (i < 3 * kRowBytes && yy >= 0 && yy < H && xx >= 0 && xx < W)
-                v = __ldg(in + ((img * H + yy) * (size_t)W + xx) * 3 + c);
-            pre[q] = v;
+        for (int r = 0; r < 3; ++r) {
+            const int yy = y + r - 1;
+            const T* row = in + (img * H + (size_t)max(min(yy, H - 1), 0)) * (size_t)W * 3;
+#pragma unroll
+            for (int q = 0; q < kLoadsPerRow; ++q) {
+                const int wi = threadIdx.x + q * 128;
+                const int fe = first + wi * kPer;
+                const bool ok = wi < kWordsPerRow && yy >= 0 && yy < H && fe >= 0 && fe < W * 3;
+                pre[r][q] = ok ? __ldg((const uint32_t*)(row + fe)) : 0u;
+                pre_valid |= (ok ? 1u : 0u) << (r * kLoadsPerRow + q);
+            }
         }
     };
     if ((int)blockIdx.x < total_segs) fetch(blockIdx.x);
@@ -191,27 +211,31 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
         const int npx = min(kSegPx, W - x0);
         __syncthreads();                                   // previous iteration finished with srow / stile
 #pragma unroll
-        for (int q = 0; q < kPre; ++q) {
-            const int i = threadIdx.x + q * 128;
-            if (i < 3 * kRowBytes) srow[i / kRowBytes][i % kRowBytes] = pre[q];
-        }
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int q = 0; q < kLoadsPerRow; ++q) {
+                const int wi = threadIdx.x + q * 128;
+                if (wi < kWordsPerRow)
+                    stage_word(&srow[r][wi * kPer], pre[r][q], (pre_valid >> (r * kLoadsPerRow + q)) & 1u, T());
+            }
         __syncthreads();
         if (seg + (int)gridDim.x < total_segs) fetch(seg + gridDim.x);
         // A fragments of both 16-pixel tiles and both k steps (16 registers), then two passes over the 64 output
-        // channels (32 accumulators live at a time keeps the kernel at 5 CTAs per SM)
+        // channels (32 accumulators live at a time keeps the kernel at 4 CTAs per SM)
         uint32_t afrag[2][2][4];
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
-            const int p0 = (warp * 32 + mt * 16 + g) * 3;          // byte offset of pixel row g in the halo row
+            const int p0 = (warp * 32 + mt * 16 + g) * 3;          // element offset of pixel row g in the halo row
             const int p1 = p0 + 8 * 3;                             // row g + 8
 #pragma unroll
             for (int ks = 0; ks < 2; ++ks) {
                 // a0: (row g, k pair 0), a1: (row g+8, pair 0), a2: (row g, pair +8), a3: (row g+8, pair +8)
                 const int o0 = koff[ks][0], o1 = koff[ks][1], o2 = koff[ks][2], o3 = koff[ks][3];
-                afrag[mt][ks][0] = pack_in(o0 >= 0 ? flat[p0 + o0] : kPad, o1 >= 0 ? flat[p0 + o1] : kPad);
-                afrag[mt][ks][1] = pack_in(o0 >= 0 ? flat[p1 + o0] : kPad, o1 >= 0 ? flat[p1 + o1] : kPad);
-                afrag[mt][ks][2] = pack_in(o2 >= 0 ? flat[p0 + o2] : kPad, o3 >= 0 ? flat[p0 + o3] : kPad);
-                afrag[mt][ks][3] = pack_in(o2 >= 0 ? flat[p1 + o2] : kPad, o3 >= 0 ? flat[p1 + o3] : kPad);
+                auto at = [&](int p, int o) -> uint32_t { return o >= 0 ? (uint32_t)flat[p + o] : 0u; };
+                afrag[mt][ks][0] = at(p0, o0) | (at(p0, o1) << 16);
+                afrag[mt][ks][1] = at(p1, o0) | (at(p1, o1) << 16);
+                afrag[mt][ks][2] = at(p0, o2) | (at(p0, o3) << 16);
+                afrag[mt][ks][3] = at(p1, o2) | (at(p1, o3) << 16);
             }
         }
         uint32_t* st32 = (uint32_t*)stile;

@@ -20,51 +20,65 @@ namespace {
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
 
-// one thread per output element (y, x, c) of the padded image
-__global__ void preprocess_kernel(const uint8_t* __restrict__ img, int H, int W, uint8_t* __restrict__ out, int h,
-                                  int w, int hp, int wp, const int* __restrict__ xf, const short* __restrict__ xc,
-                                  const int* __restrict__ yf, const short* __restrict__ yc, size_t img_stride,
-                                  size_t out_stride) {
-    const int e = blockIdx.x * blockDim.x + threadIdx.x;      // element within the padded row (x*3 + c)
+// one thread per output PIXEL (y, x) of the padded image: the three channels share the tap indices and weights
+__global__ void __launch_bounds__(128) preprocess_kernel(const uint8_t* __restrict__ img, int H, int W,
+                                                         uint8_t* __restrict__ out, int h, int w, int hp, int wp,
+                                                         const int* __restrict__ xf, const short* __restrict__ xc,
+                                                         const int* __restrict__ yf, const short* __restrict__ yc,
+                                                         size_t img_stride, size_t out_stride) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (e >= wp * 3) return;
+    if (x >= wp) return;
     img += blockIdx.z * img_stride;
     out += blockIdx.z * out_stride;
-    uint8_t* o = out + (size_t)y * wp * 3 + e;
-    const int x = e / 3, c = e - x * 3;
+    uint8_t* o = out + ((size_t)y * wp + x) * 3;
     if (y >= h || x >= w) {
-        *o = 128;                                               // padValue, src/body.py:29
+        o[0] = o[1] = o[2] = 128;                               // padValue, src/body.py:29
         return;
     }
     const int x0 = xf[x], y0 = yf[y];
-    int cx[4];
+    int cx[4], wx[4];
+    const short4 xw4 = *(const short4*)(xc + x * 4);
+    wx[0] = xw4.x; wx[1] = xw4.y; wx[2] = xw4.z; wx[3] = xw4.w;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) cx[j] = clampi(x0 + j, 0, W - 1) * 3 + c;
-    int hor[4];
+    for (int j = 0; j < 4; ++j) cx[j] = clampi(x0 + j, 0, W - 1) * 3;
+    int hor[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const uint8_t* row = img + (size_t)clampi(y0 + k, 0, H - 1) * W * 3;
-        int s = 0;
+        int s0 = 0, s1 = 0, s2 = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) s += (int)row[cx[j]] * (int)xc[x * 4 + j];
-        hor[k] = s;
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t* px = row + cx[j];
+            s0 += (int)__ldg(px) * wx[j];
+            s1 += (int)__ldg(px + 1) * wx[j];
+            s2 += (int)__ldg(px + 2) * wx[j];
+        }
+        hor[k][0] = s0; hor[k][1] = s1; hor[k][2] = s2;
     }
-    int r;
+    const short4 yw4 = *(const short4*)(yc + y * 4);
+    const int wyi[4] = {yw4.x, yw4.y, yw4.z, yw4.w};
+    const float sc = 1.0f / (2048.0f * 2048.0f);
+    float wyf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wyf[k] = __fmul_rn((float)wyi[k], sc);
     const int nvec = ((w * 3) / 8) * 8;                         // OpenCV: 8-lane SIMD body, scalar tail
-    if (e < nvec) {
-        const float sc = 1.0f / (2048.0f * 2048.0f);
-        float acc = __fmul_rn((float)hor[3], __fmul_rn((float)yc[y * 4 + 3], sc));
 #pragma unroll
-        for (int k = 2; k >= 0; --k)
-            acc = __fadd_rn(acc, __fmul_rn((float)hor[k], __fmul_rn((float)yc[y * 4 + k], sc)));
-        r = __float2int_rn(acc);
-    } else {
-        long long s = 0;
+    for (int c = 0; c < 3; ++c) {
+        int r;
+        if (x * 3 + c < nvec) {
+            float acc = __fmul_rn((float)hor[3][c], wyf[3]);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) s += (long long)hor[k] * (long long)yc[y * 4 + k];
-        r = (int)((s + (1ll << 21)) >> 22);
+            for (int k = 2; k >= 0; --k) acc = __fadd_rn(acc, __fmul_rn((float)hor[k][c], wyf[k]));
+            r = __float2int_rn(acc);
+        } else {
+            long long s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += (long long)hor[k][c] * (long long)wyi[k];
+            r = (int)((s + (1ll << 21)) >> 22);
+        }
+        o[c] = (uint8_t)clampi(r, 0, 255);
     }
-    *o = (uint8_t)clampi(r, 0, 255);
 }
 
 // pass 1: tmp[c][r][x] = sum_k xw[x][k] * src[r][xfirst[x]+k][c]      (one scale)
@@ -167,26 +181,27 @@ __global__ void __launch_bounds__(128) upsample_y_blocked_kernel(const __grid_co
     const int yb = blockIdx.y;
     const int c = blockIdx.z * blockDim.y + threadIdx.y;
     if (x >= W || c >= CT) return;
-    float4 acc[kTY];
+    // accumulators as float2 pairs: sm_100's packed FFMA2 (__ffma2_rn) retires two IEEE fp32 FMAs per issue slot --
+    // bit-identical to two fmaf, and this kernel is FMA-issue bound (28 FMAs per output element)
+    float2 acc[kTY][2];
 #pragma unroll
-    for (int i = 0; i < kTY; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < kTY; ++i) acc[i][0] = acc[i][1] = make_float2(0.f, 0.f);
     for (int s = 0; s < p.n_scales; ++s) {
         const int f0 = p.first[s][yb], R = p.rows[s][yb], rs = p.rs[s];
         const float* t = p.tmp[s] + ((size_t)c * p.ho[s] + f0) * W + x;
         const float4* wt = (const float4*)(p.w[s] + (size_t)yb * rs * kTY);
         for (int r = 0; r < R; ++r) {
             const float4 v = *(const float4*)(t + (size_t)r * W);
+            const float2 vlo = make_float2(v.x, v.y), vhi = make_float2(v.z, v.w);
 #pragma unroll
             for (int q = 0; q < kTY / 4; ++q) {
                 const float4 w4 = __ldg(wt + r * (kTY / 4) + q);
                 const float ws[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float4& a = acc[q * 4 + j];
-                    a.x = fmaf(ws[j], v.x, a.x);
-                    a.y = fmaf(ws[j], v.y, a.y);
-                    a.z = fmaf(ws[j], v.z, a.z);
-                    a.w = fmaf(ws[j], v.w, a.w);
+                    const float2 w2 = make_float2(ws[j], ws[j]);
+                    acc[q * 4 + j][0] = __ffma2_rn(w2, vlo, acc[q * 4 + j][0]);
+                    acc[q * 4 + j][1] = __ffma2_rn(w2, vhi, acc[q * 4 + j][1]);
                 }
             }
         }
@@ -194,7 +209,8 @@ __global__ void __launch_bounds__(128) upsample_y_blocked_kernel(const __grid_co
     float* o = out + ((size_t)c * H + (size_t)yb * kTY) * W + x;
 #pragma unroll
     for (int i = 0; i < kTY; ++i)
-        if (yb * kTY + i < H) *(float4*)(o + (size_t)i * W) = acc[i];
+        if (yb * kTY + i < H)
+            *(float4*)(o + (size_t)i * W) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
 }
 
 }  // namespace
@@ -202,8 +218,8 @@ __global__ void __launch_bounds__(128) upsample_y_blocked_kernel(const __grid_co
 void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t* out, int h, int w, int hp, int wp,
                                const int* x_first, const short* x_coef, const int* y_first, const short* y_coef,
                                cudaStream_t stream) {
-    dim3 grid(cdiv(wp * 3, 256), hp, n);
-    preprocess_kernel<<<grid, 256, 0, stream>>>(img, H, W, out, h, w, hp, wp, x_first, x_coef, y_first, y_coef,
+    dim3 grid(cdiv(wp, 128), hp, n);
+    preprocess_kernel<<<grid, 128, 0, stream>>>(img, H, W, out, h, w, hp, wp, x_first, x_coef, y_first, y_coef,
                                                 (size_t)H * W * 3, (size_t)hp * wp * 3);
     OPB_CUDA(cudaGetLastError());
 }

@@ -186,6 +186,22 @@ def test_hand_many_aspect_ratios_evict_cnn_plans():
         assert np.array_equal(a, b)
 
 
+def test_hand_256_crops_chunked_equals_single_crops():
+    """BASELINE config 3 shape: 256 crops of 368x368 in one call (chunks of 32 over two sessions) must give exactly
+    the per-crop results (single scale here to keep the test short; the 4-scale path is timed by tools/bench_hand_c3.py)."""
+    from pytorch_openpose_b200 import Hand
+    sd = O.make_weights("hand", 5, "kaiming")
+    hand = Hand(sd, scale_search=[0.5])
+    crops = np.random.default_rng(12).integers(0, 256, (256, 368, 368, 3), dtype=np.uint8)
+    crops[1::2] = crops[1::2] // 2 + 60
+    peaks = hand(crops)
+    assert peaks.shape == (256, 21, 3)
+    for i in (0, 31, 32, 100, 255):
+        assert np.array_equal(hand(crops[i]), peaks[i])
+    maps = hand.last_maps(crops[255].shape)[0]
+    assert np.array_equal(peaks[255], O.hand_postprocess(maps.astype(np.float64)))
+
+
 def test_synthetic_scene_through_public_api_grouping(golden):
     """The crowded-scene config (BASELINE config 5): 50 people injected at the map boundary -> identical result."""
     from tests import gpu_util as G
