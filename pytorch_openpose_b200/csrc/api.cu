@@ -150,7 +150,7 @@ static UpTables make_up_tables(TableSlab& pool, int H, int W, const ScaleDims& d
     t.xw = pool.add(wx);
     t.yw = pool.add(wy);
     // strips of 16 output rows: first source row, number of source rows, dense weights (x 1/n_scales)
-    const int TY = 16, nyb = (H + TY - 1) / TY;
+    const int TY = kUpStrip, nyb = (H + TY - 1) / TY;
     std::vector<int> bf(nyb), br(nyb);
     int rs = 1;
     for (int b = 0; b < nyb; ++b) {

@@ -101,6 +101,7 @@ void preprocess_f32_launch(const void* frames, bool frames_u8_hwc, int n, int H,
                            cudaStream_t stream);
 void blur5_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream);
 
+constexpr int kUpStrip = 8;          // output rows per register-blocked strip of the y upsample pass (tables + kernel)
 struct UpsampleScale {
     const float* src;         // fp32 NHWC net output
     int ho, wo, cstride;      // source dims and per-pixel stride (elements)
