@@ -152,23 +152,64 @@ def body_pose(candidate, subset):
     return pose, chosen
 
 
-def _hands_into(pose60, frame, candidate, subset, chosen, hand_estimation):
-    """srcmx/MotionEstimation.py:160-194: hands of the chosen person only, left crops mirrored."""
+def _hand_jobs(frame, candidate, subset, chosen):
+    """srcmx/MotionEstimation.py:160-190: boxes of the chosen person only -> [(crop, x, y, w, is_left)], left crops
+    mirrored (the hand net detects right hands)."""
     for i in range(len(subset)):
         if i != chosen:
             subset[i, :] = -1
+    jobs = []
     for x, y, w, is_left in util.handDetect(candidate, subset, frame):
         crop = frame[y:y + w, x:x + w, :]
-        if is_left:
-            peaks = hand_estimation(np.ascontiguousarray(crop[:, ::-1, :]))
-            peaks[:, 0] = np.where(peaks[:, 0] == 0, peaks[:, 0], w - peaks[:, 0] - 1 + x)
-            peaks[:, 1] = np.where(peaks[:, 1] == 0, peaks[:, 1], peaks[:, 1] + y)
-            pose60[18:39, :] = peaks
-        else:
-            peaks = hand_estimation(crop)
-            peaks[:, 0] = np.where(peaks[:, 0] == 0, peaks[:, 0], peaks[:, 0] + x)
-            peaks[:, 1] = np.where(peaks[:, 1] == 0, peaks[:, 1], peaks[:, 1] + y)
-            pose60[39:60, :] = peaks
+        jobs.append((np.ascontiguousarray(crop[:, ::-1, :]) if is_left else np.ascontiguousarray(crop), x, y, w, is_left))
+    return jobs
+
+
+def _apply_hand(pose60, peaks, x, y, w, is_left):
+    """srcmx/MotionEstimation.py:185-194: crop coordinates -> frame coordinates; exact zeros mean "missing"."""
+    if is_left:
+        peaks[:, 0] = np.where(peaks[:, 0] == 0, peaks[:, 0], w - peaks[:, 0] - 1 + x)
+        peaks[:, 1] = np.where(peaks[:, 1] == 0, peaks[:, 1], peaks[:, 1] + y)
+        pose60[18:39, :] = peaks
+    else:
+        peaks[:, 0] = np.where(peaks[:, 0] == 0, peaks[:, 0], peaks[:, 0] + x)
+        peaks[:, 1] = np.where(peaks[:, 1] == 0, peaks[:, 1], peaks[:, 1] + y)
+        pose60[39:60, :] = peaks
+
+
+class _HandPool(object):
+    """Hand crops of a whole body batch in flight on several sessions of a `Hand` (every crop has its own size, so
+    each is its own submit); results are applied in submission order per session."""
+
+    def __init__(self, hand, n):
+        self.hand = hand
+        self.sessions = _job_sessions(hand, n)
+        self.busy = [None] * n
+        self.turn = 0
+
+    def _retire(self, i):
+        if self.busy[i] is not None:
+            pose60, x, y, w, is_left = self.busy[i]
+            _apply_hand(pose60, self.hand.collect(self.sessions[i])[0], x, y, w, is_left)
+            self.busy[i] = None
+
+    def submit(self, pose60, crop, x, y, w, is_left):
+        i = self.turn
+        self.turn = (self.turn + 1) % len(self.sessions)
+        self._retire(i)
+        if crop.shape[0] == 0 or crop.shape[1] == 0:
+            raise ZeroDivisionError("float division by zero")            # src/hand.py:32 on an empty box
+        self.hand.submit(crop, self.sessions[i])
+        self.busy[i] = (pose60, x, y, w, is_left)
+
+    def drain(self):
+        for i in range(len(self.sessions)):
+            self._retire(i)
+
+
+def _hands_into(pose60, frame, candidate, subset, chosen, hand_estimation):
+    for crop, x, y, w, is_left in _hand_jobs(frame, candidate, subset, chosen):
+        _apply_hand(pose60, hand_estimation(crop), x, y, w, is_left)
 
 
 def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, hand_estimation=None, mode="body",
@@ -191,6 +232,9 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
     mat = np.zeros((src.count, joints, 3))
     outname = os.path.split(outpath)[1]
     done = 0
+    hand_pool = None
+    if mode == "bodyhand" and pipelined and hasattr(hand_estimation, "submit") and hasattr(hand_estimation, "net"):
+        hand_pool = _HandPool(hand_estimation, 4)
 
     def finish(frames, first, results):
         nonlocal done
@@ -200,7 +244,11 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
             pose, chosen = body_pose(candidate, subset)
             mat[first + f, :18, :] = pose
             if mode == "bodyhand" and chosen is not None:
-                _hands_into(mat[first + f], frames[f], candidate, subset, chosen, hand_estimation)
+                if hand_pool is not None:
+                    for job in _hand_jobs(frames[f], candidate, subset, chosen):
+                        hand_pool.submit(mat[first + f], *job)
+                else:
+                    _hands_into(mat[first + f], frames[f], candidate, subset, chosen, hand_estimation)
             if (first + f) % 100 == 0:
                 log("%s-%d/%d" % (outname, first + f, src.count))
             done += 1
@@ -242,6 +290,8 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
     else:
         for frames, first in src:
             finish(frames, first, [body_estimation(frames[f]) for f in range(len(frames))])
+    if hand_pool is not None:
+        hand_pool.drain()
     joblib.dump(mat, outpath)
     log("%s is saved!" % outpath)
     return mat

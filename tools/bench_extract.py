@@ -45,6 +45,45 @@ for k in (1, W):
                                             log=lambda m: None, decode_workers=k, stats=st)
     job[k] = len(mat) / (time.perf_counter() - t0)
     job["seconds_%d" % k] = {a: round(b, 3) for a, b in st.items()}
+
+# ---- body + two hands per frame (the reference's 'bodyhand' mode).  Random-init weights find nobody, so every frame
+# gets one synthetic person whose arm joints (and therefore both hand boxes, ~150-200 px, a new size every frame)
+# move with the frame index; the hand network and its post-processing really run on those crops.
+from pytorch_openpose_b200 import Hand          # noqa: E402
+
+
+class BodyP(Body):
+    n = 0
+
+    def _person(self):
+        k = BodyP.n
+        BodyP.n += 1
+        joints = {2: (500, 200), 3: (430 + k % 17, 330), 4: (380 + 2 * (k % 13), 460 + k % 19),
+                  5: (780, 200), 6: (850 - k % 16, 330), 7: (900 - 2 * (k % 11), 460 + k % 23)}
+        cand = np.zeros((8, 4))
+        row = -np.ones(20)
+        for i, (j, (x, y)) in enumerate(sorted(joints.items())):
+            cand[i] = (x, y, 0.9, i)
+            row[j] = i
+        row[18], row[19] = 6.0, 6
+        return cand, row[None].copy()
+
+    def collect_batch(self, session=None):
+        return [self._person() for _ in Body.collect_batch(self, session)]
+
+
+bodyp = BodyP(body.net_weights if hasattr(body, "net_weights") else O.make_weights("body", 0), scale_search=[0.5, 1.0, 1.5, 2.0])
+hand = Hand(O.make_weights("hand", 0))
+bh = {}
+for k in (W,):
+    extract.extract_motion_from_video(path, os.path.join(d, "wh.pkl"), None, bodyp, hand, mode="bodyhand", batch=8,
+                                      sessions=3, log=lambda m: None, decode_workers=k)
+    t0 = time.perf_counter()
+    mat = extract.extract_motion_from_video(path, os.path.join(d, "oh.pkl"), None, bodyp, hand, mode="bodyhand", batch=8,
+                                            sessions=3, log=lambda m: None, decode_workers=k)
+    bh[k] = len(mat) / (time.perf_counter() - t0)
+    bh["frames_with_both_hands"] = int(((mat[:, 18:39, 2] > 0).any(1) & (mat[:, 39:, 2] > 0).any(1)).sum())
+del bodyp, hand
 del body
 bb = Batch_body(O.make_weights("body", 0))
 extract.batch_body_extraction(path, os.path.join(d, "wb.pkl"), 16, None, bb, log=lambda m: None)
@@ -55,5 +94,5 @@ for k in (1, W):
     mat = extract.batch_body_extraction(path, os.path.join(d, "ob.pkl"), 16, None, bb, log=lambda m: None, decode_workers=k)
     bjob[k] = len(mat) / (time.perf_counter() - t0)
 print(json.dumps({"metric": "extraction_job_frames_per_sec_720p", "frames": N, "decode_only_fps_by_workers": dec,
-                  "body_4scale_job_fps_by_workers": job, "batch_body_job_fps_by_workers": bjob, "host_cores": os.cpu_count(),
+                  "body_4scale_job_fps_by_workers": job, "bodyhand_4scale_job_fps_by_workers": bh, "batch_body_job_fps_by_workers": bjob, "host_cores": os.cpu_count(),
                   "note": "cv2.VideoCapture decode threads (MJPG 720p); wall clock incl. decode, H2D, D2H, file write"}))
