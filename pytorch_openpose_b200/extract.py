@@ -50,7 +50,7 @@ class FrameBatches(object):
     one thread each (seek with CAP_PROP_POS_FRAMES); batches then arrive in whatever order they are decoded -- every
     batch carries its first frame index -- and frames past the container's reported count are not read."""
 
-    def __init__(self, videopath, recpoint=None, batch=8, depth=4, pinned=False, workers=1):
+    def __init__(self, videopath, recpoint=None, batch=8, depth=4, pinned=False, workers=1, pad_last=False):
         import cv2
         probe = cv2.VideoCapture(videopath)
         if not probe.isOpened():
@@ -58,6 +58,9 @@ class FrameBatches(object):
         self.count = int(probe.get(cv2.CAP_PROP_FRAME_COUNT))
         probe.release()
         self.videopath, self.recpoint, self.batch, self.pinned = videopath, recpoint, batch, pinned
+        # pad_last: a short final batch is filled up with copies of its last frame and yielded at full size as
+        # (frames, first, n_valid), so that the estimator never sees a new batch size (= a new CNN plan) at a video's end
+        self.pad_last = pad_last
         self.hold = max(depth - 2, 1)
         self.workers = max(1, int(workers))
         self._q = queue.Queue()
@@ -106,6 +109,8 @@ class FrameBatches(object):
                     self._q.put((w, cur, fill, first))
                     cur = None
             if cur is not None and fill:
+                if self.pad_last:
+                    ring["bufs"][cur][0][fill:] = ring["bufs"][cur][0][fill - 1]
                 self._q.put((w, cur, fill, first))
             self._q.put(None)
         except BaseException as e:                     # surface decode errors in the consumer
@@ -127,7 +132,10 @@ class FrameBatches(object):
             if len(held) > self.hold:                  # the consumer is done with the oldest buffer
                 ow, oc = held.pop(0)
                 self._rings[ow]["free"].put(oc)
-            yield self._rings[w]["bufs"][cur][0][:fill], first
+            if self.pad_last:
+                yield self._rings[w]["bufs"][cur][0], first, fill
+            else:
+                yield self._rings[w]["bufs"][cur][0][:fill], first
 
 
 def _job_sessions(estimator, n):
@@ -224,7 +232,8 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
     if pinned is None:
         pinned = pipelined
     try:
-        src = FrameBatches(videopath, recpoint, batch=batch, depth=sessions + 3, pinned=pinned, workers=decode_workers)
+        src = FrameBatches(videopath, recpoint, batch=batch, depth=sessions + 3, pinned=pinned, workers=decode_workers,
+                           pad_last=pipelined)
     except FileNotFoundError as e:
         log(str(e))
         return None
@@ -260,12 +269,12 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
         pending = []                                                   # (session, frames, first)
 
         def retire():
-            s, fr, fi = pending.pop(0)
+            s, fr, fi, nv = pending.pop(0)
             t = time.perf_counter()
             res = body_estimation.collect_batch(s)
             clock["collect_wait"] += time.perf_counter() - t
             t = time.perf_counter()
-            finish(fr, fi, res)
+            finish(fr, fi, res[:nv])
             clock["records"] += time.perf_counter() - t
 
         it = iter(src)
@@ -275,14 +284,14 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
             clock["decode_wait"] += time.perf_counter() - t
             if item is None:
                 break
-            frames, first = item
+            frames, first, n_valid = item
             if len(pending) == sessions:
                 retire()
             s = next(c for c in ss if all(c is not p[0] for p in pending))
             t = time.perf_counter()
             body_estimation.submit_batch(frames, s, where=2 if pinned else 0)
             clock["submit"] += time.perf_counter() - t
-            pending.append((s, frames, first))
+            pending.append((s, frames, first, n_valid))
         while pending:
             retire()
         if stats is not None:
@@ -312,7 +321,7 @@ def batch_body_extraction(videopath, outpath, batch_size, recpoint, batch_body_m
     pipelined = hasattr(batch_body_model, "submit_frames")
     try:
         src = FrameBatches(videopath, recpoint, batch=batch_size, depth=sessions + 3 if pipelined else 4, pinned=pipelined,
-                           workers=decode_workers)
+                           workers=decode_workers, pad_last=pipelined)
     except FileNotFoundError as e:
         log(str(e))
         return None
@@ -332,15 +341,15 @@ def batch_body_extraction(videopath, outpath, batch_size, recpoint, batch_body_m
     if pipelined:
         ss = _job_sessions(batch_body_model, sessions)
         pending = []
-        for frames, first in src:
+        for frames, first, n_valid in src:
             if len(pending) == sessions:
-                s, fi = pending.pop(0)
-                finish(fi, batch_body_model.collect(s))
+                s, fi, nv = pending.pop(0)
+                finish(fi, batch_body_model.collect(s)[:nv])
             s = next(c for c in ss if all(c is not p[0] for p in pending))
             batch_body_model.submit_frames(frames, s, where=2)
-            pending.append((s, first))
-        for s, fi in pending:
-            finish(fi, batch_body_model.collect(s))
+            pending.append((s, first, n_valid))
+        for s, fi, nv in pending:
+            finish(fi, batch_body_model.collect(s)[:nv])
     else:
         for frames, first in src:
             finish(first, batch_body_model(to_tensor(frames)))
