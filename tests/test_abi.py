@@ -66,3 +66,26 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.OpbError) as e:
         _lib.context(0)
     assert e.value.code == _lib.OPB_ERR_NO_DEVICE
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++ / torch types) and a C program must link against
+    the shared library and call into it (no GPU needed for these calls)."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include <stdio.h>\n#include "openpose_b200.h"\n'
+                   'int main(void) {\n'
+                   '    opb_context* ctx = 0;\n'
+                   '    int h, w, hp, wp;\n'
+                   '    if (opb_abi_version() != OPB_ABI_VERSION) return 1;\n'
+                   '    if (opb_scale_dims(720, 1280, 0.5, &h, &w, &hp, &wp) != OPB_OK) return 2;\n'
+                   '    printf("%d %d %d %d %d\\n", h, w, hp, wp, opb_context_create(0, &ctx));\n'
+                   '    return 0;\n}\n')
+    libdir = os.path.join(ROOT, "pytorch_openpose_b200")
+    exe = str(tmp_path / "abi")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-L", libdir, "-lopenpose_b200", "-Wl,-rpath," + libdir, "-o", exe], check=True)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout.split()
+    assert out[:4] == ["184", "327", "184", "328"]                    # SURVEY.md 8: C2 scale 0.5 -> 327x184 padded 328x184
+    if not torch.cuda.is_available():
+        assert int(out[4]) == _lib.OPB_ERR_NO_DEVICE
