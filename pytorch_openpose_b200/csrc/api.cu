@@ -197,6 +197,14 @@ struct FrameKey {
 struct FramePlan {
     DevPool pool;
     FrameKey key;
+    // the device work of one submit (everything between the input upload and the "done" event) as a CUDA graph:
+    // captured on the third use of the plan, re-captured when a session buffer it points into has moved
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_gen = 0;
+    int uses = 0;
+    ~FramePlan() {
+        if (graph) cudaGraphExecDestroy(graph);
+    }
     std::vector<ScaleDims> dims;
     std::vector<U8Taps> u8taps;
     std::vector<F32Taps> f32taps;
@@ -290,6 +298,7 @@ struct opb_session {
     // size-dependent work buffers, grown to the largest frame seen and shared by all plans of the session
     enum { AR_IMG, AR_SCRATCH, AR_HEAT, AR_PAF, AR_LABELS, AR_SUMS, AR_PEAKS, AR_BLUR, AR_COUNT };
     struct Arena { void* p = nullptr; size_t cap = 0; } arena[AR_COUNT];
+    uint64_t buffer_gen = 1;         // bumped whenever an arena or a pinned result buffer is reallocated
     ~opb_session() {
         plans.clear();
         net_plans.clear();
@@ -311,12 +320,14 @@ static void ensure_host(opb_session* s, int frames, size_t hand_doubles) {
         if (s->host) cudaFreeHost(s->host);
         OPB_CUDA(cudaMallocHost((void**)&s->host, need));
         s->host_bytes = need;
+        ++s->buffer_gen;
     }
     const size_t hneed = hand_doubles * sizeof(double);
     if (s->hand_host_bytes < hneed) {
         if (s->hand_host) cudaFreeHost(s->hand_host);
         OPB_CUDA(cudaMallocHost((void**)&s->hand_host, hneed));
         s->hand_host_bytes = hneed;
+        ++s->buffer_gen;
     }
 }
 static void ensure_staging(opb_session* s, size_t bytes) {
@@ -360,6 +371,7 @@ static void* arena_get(opb_session* s, int which, size_t bytes) {
         const size_t want = bytes + bytes / 4 + 256;
         OPB_CUDA(cudaMalloc(&a.p, want));
         a.cap = want;
+        ++s->buffer_gen;
     }
     return a.p;
 }
@@ -428,6 +440,41 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     FramePlan* raw = fp.get();
     s->plans[key] = std::move(fp);
     return raw;
+}
+
+// Runs `enqueue` (kernel launches, memsets and result copies on the session's stream) either directly or, once the plan
+// has been used a few times, as one CUDA graph launch: a frame is ~110 small dependent launches, and for the small
+// default configuration (640x480, one scale) the launch gaps, not the kernels, are most of the latency.
+template <typename F>
+static void run_or_replay(opb_session* s, FramePlan* fp, F&& enqueue) {
+    static const bool no_graph = getenv("OPB_NO_GRAPH") != nullptr;
+    cudaStream_t st = s->stream;
+    ++fp->uses;
+    if (no_graph || s->prof.on || fp->uses < 3) {       // first uses run eagerly (lazy module loading, attributes)
+        enqueue();
+        return;
+    }
+    if (!fp->graph || fp->graph_gen != s->buffer_gen) {
+        if (fp->graph) {
+            cudaGraphExecDestroy(fp->graph);
+            fp->graph = nullptr;
+        }
+        cudaGraph_t g = nullptr;
+        OPB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue();
+        } catch (...) {
+            cudaStreamEndCapture(st, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        OPB_CUDA(cudaStreamEndCapture(st, &g));
+        const cudaError_t e = cudaGraphInstantiate(&fp->graph, g, 0);
+        cudaGraphDestroy(g);
+        OPB_CUDA(e);
+        fp->graph_gen = s->buffer_gen;
+    }
+    OPB_CUDA(cudaGraphLaunch(fp->graph, st));
 }
 
 static void upload_image(opb_session* s, FramePlan* fp, const uint8_t* img, int where, size_t bytes) {
@@ -501,7 +548,10 @@ static void body_post_enqueue(opb_session* s, FramePlan* fp, int n, int H, int W
         OPB_CUDA(cudaMemcpyAsync(h->subset, bp.lb.subset, sizeof(h->subset), cudaMemcpyDeviceToHost, st));
         s->prof.mark(st, "d2h");
     }
-    OPB_CUDA(cudaEventRecord(s->done, st));
+}
+
+static void finish_submit(opb_session* s, FramePlan* fp) {
+    OPB_CUDA(cudaEventRecord(s->done, s->stream));
     s->net->ctx->launches += fp->launches_per_frame;
 }
 
@@ -518,11 +568,14 @@ static void body_submit(opb_session* s, const uint8_t* img, int where, int n, in
     s->prof.mark(st, "start");
     upload_image(s, fp, img, where, (size_t)n * H * W * 3);
     s->prof.mark(st, "h2d");
-    run_front(s, fp, n, H, W);
-    run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
-    run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
-    s->prof.mark(st, "upsample_avg");
-    body_post_enqueue(s, fp, n, H, W);
+    run_or_replay(s, fp, [&] {
+        run_front(s, fp, n, H, W);
+        run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
+        run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
+        s->prof.mark(st, "upsample_avg");
+        body_post_enqueue(s, fp, n, H, W);
+    });
+    finish_submit(s, fp);
 }
 
 // float front end of the batched estimators: resize (body only) - 0.5, zero pad, bf16 HWC3 -> CNN
@@ -550,13 +603,16 @@ static void batch_body_submit(opb_session* s, const void* frames, bool u8, int w
     s->prof.mark(st, "start");
     upload_image(s, fp, (const uint8_t*)frames, where, (size_t)n * H * W * 3 * (u8 ? 1 : sizeof(float)));
     s->prof.mark(st, "h2d");
-    run_front_f32(s, fp, n, H, W);
-    run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
-    run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
-    s->prof.mark(st, "upsample_avg");
-    blur5_launch(fp->heat_avg, fp->blurred, n * 19, H, W, st);                                     // utilmx.py:261-263
-    s->prof.mark(st, "blur5");
-    body_post_enqueue(s, fp, n, H, W);
+    run_or_replay(s, fp, [&] {
+        run_front_f32(s, fp, n, H, W);
+        run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
+        run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
+        s->prof.mark(st, "upsample_avg");
+        blur5_launch(fp->heat_avg, fp->blurred, n * 19, H, W, st);                                 // utilmx.py:261-263
+        s->prof.mark(st, "blur5");
+        body_post_enqueue(s, fp, n, H, W);
+    });
+    finish_submit(s, fp);
 }
 
 // returns the first non-OK per-frame status (OPB_ERR_SUBSET_INDEX mirrors the reference's IndexError)
@@ -630,15 +686,16 @@ static void hand_submit(opb_session* s, const uint8_t* img, int where, int n, in
     s->prof.mark(st, "start");
     upload_image(s, fp, img, where, (size_t)n * H * W * 3);
     s->prof.mark(st, "h2d");
-    run_front(s, fp, n, H, W);
-    run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);
-    s->prof.mark(st, "upsample_avg");
-    hand_peaks_launch2(fp->heat_avg, n, 22, H, W, 0.03, fp->hb, nullptr, st);        // thre, src/hand.py:31
-    s->prof.mark(st, "hand_peaks");
-    OPB_CUDA(cudaMemcpyAsync(s->hand_host, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    s->prof.mark(st, "d2h");
-    OPB_CUDA(cudaEventRecord(s->done, st));
-    s->net->ctx->launches += fp->launches_per_frame;
+    run_or_replay(s, fp, [&] {
+        run_front(s, fp, n, H, W);
+        run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);
+        s->prof.mark(st, "upsample_avg");
+        hand_peaks_launch2(fp->heat_avg, n, 22, H, W, 0.03, fp->hb, nullptr, st);    // thre, src/hand.py:31
+        s->prof.mark(st, "hand_peaks");
+        OPB_CUDA(cudaMemcpyAsync(s->hand_host, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        s->prof.mark(st, "d2h");
+    });
+    finish_submit(s, fp);
 }
 
 // Batch_hand.__call__ (srcmx/Batch_model.py:366-406)
@@ -656,17 +713,18 @@ static void batch_hand_submit(opb_session* s, const void* crops, bool u8, int wh
     s->prof.mark(st, "start");
     upload_image(s, fp, (const uint8_t*)crops, where, (size_t)n * H * W * 3 * (u8 ? 1 : sizeof(float)));
     s->prof.mark(st, "h2d");
-    run_front_f32(s, fp, n, H, W);
-    run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);                                    // x8 bicubic, :377
-    s->prof.mark(st, "upsample_avg");
-    blur5_launch(fp->heat_avg, fp->blurred, n * 22, H, W, st);                                     // :378
-    s->prof.mark(st, "blur5");
-    hand_peaks_blurred_launch(fp->blurred, n, 22, H, W, 0.035f, fp->hb, st);                       // thre, :361
-    s->prof.mark(st, "hand_peaks");
-    OPB_CUDA(cudaMemcpyAsync(s->hand_host, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    s->prof.mark(st, "d2h");
-    OPB_CUDA(cudaEventRecord(s->done, st));
-    s->net->ctx->launches += fp->launches_per_frame;
+    run_or_replay(s, fp, [&] {
+        run_front_f32(s, fp, n, H, W);
+        run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);                                // x8 bicubic, :377
+        s->prof.mark(st, "upsample_avg");
+        blur5_launch(fp->heat_avg, fp->blurred, n * 22, H, W, st);                                 // :378
+        s->prof.mark(st, "blur5");
+        hand_peaks_blurred_launch(fp->blurred, n, 22, H, W, 0.035f, fp->hb, st);                   // thre, :361
+        s->prof.mark(st, "hand_peaks");
+        OPB_CUDA(cudaMemcpyAsync(s->hand_host, fp->hb.peaks, (size_t)n * 63 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        s->prof.mark(st, "d2h");
+    });
+    finish_submit(s, fp);
 }
 
 }  // namespace opb
