@@ -256,19 +256,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                         for (int j = 0; j < 32; j += 4)
                             if (c0 + j < n_valid) *(float4*)(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
                     } else {
-                        __nv_bfloat16* o = (__nv_bfloat16*)q.out + out_off + c0;
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (c0 + j < n_valid) {
-                                __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-                                __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-                                __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-                                __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-                                uint4 u;
-                                u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1; u.z = *(uint32_t*)&h2; u.w = *(uint32_t*)&h3;
-                                *(uint4*)(o + j) = u;
-                            }
-                        }
+                        store_bf16x32((__nv_bfloat16*)q.out + out_off + c0, f, n_valid - c0);
                     }
                 }
             }

@@ -173,6 +173,44 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
         : "memory");
 }
 
+// ---- epilogue stores -------------------------------------------------------------------------------------
+// 32 fp32 values -> bf16, written as 256-bit stores (sm_100: STG.256) where the destination is 32-byte aligned and
+// both 8-channel halves are wanted: whole 32-byte sectors instead of two 16-byte halves from separate instructions.
+__device__ __forceinline__ uint4 pack_bf16x8(const float* f) {
+    __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
+    __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
+    __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
+    __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
+    uint4 u;
+    u.x = *(uint32_t*)&h0; u.y = *(uint32_t*)&h1; u.z = *(uint32_t*)&h2; u.w = *(uint32_t*)&h3;
+    return u;
+}
+__device__ __forceinline__ void st_global_256(void* p, uint4 a, uint4 b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+                 : "memory");
+}
+// o: first of 32 consecutive bf16 channels; channels at index >= n_left are not written (n_left is a multiple of 8)
+__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* o, const float (&f)[32], int n_left) {
+    const bool aligned32 = (reinterpret_cast<uintptr_t>(o) & 31) == 0;
+#pragma unroll
+    for (int j = 0; j < 32; j += 16) {
+        if (j >= n_left) break;
+        const uint4 a = pack_bf16x8(&f[j]);
+        if (j + 8 < n_left) {
+            const uint4 b = pack_bf16x8(&f[j + 8]);
+            if (aligned32) {
+                st_global_256(o + j, a, b);
+            } else {
+                *(uint4*)(o + j) = a;
+                *(uint4*)(o + j + 8) = b;
+            }
+        } else {
+            *(uint4*)(o + j) = a;
+        }
+    }
+}
+
 // ---- CTA-pair (cta_group::2) variants -------------------------------------------------------------------
 // A cluster of two CTAs (same TPC) cooperates on one UMMA: M = 256 (128 rows per CTA, each from its own shared
 // memory and into its own TMEM), N split across the pair (each CTA stages N/2 weight rows).  TMA loads of both CTAs
