@@ -242,12 +242,22 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
         const int tx = row & 7, ty = row >> 3;
         int acc = 0;
         uint32_t acc_phase = 0;
+        int bias_loaded[kAccStages];
+#pragma unroll
+        for (int a = 0; a < kAccStages; ++a) bias_loaded[a] = -1;
         for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
             const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
             const QProb& q = p.prob[tc.pi];
             float* bias_s = sbias + acc * BLOCK_N;
-            if (ep_tid < BLOCK_N) bias_s[ep_tid] = __ldg(q.bias + tc.n0 + ep_tid);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
+            // the bias slice changes only with the problem / n tile: reloading it for every tile put a global load and a
+            // barrier at the head of each epilogue, which is what paced the short-K (1x1, 3x3) layers
+            const int bias_key = (tc.pi << 16) | tc.n0;
+            if (bias_loaded[acc] != bias_key) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // nobody still reads this slot (two tiles back)
+                if (ep_tid < BLOCK_N) bias_s[ep_tid] = __ldg(q.bias + tc.n0 + ep_tid);
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // bias visible to the 4 epilogue warps
+                bias_loaded[acc] = bias_key;
+            }
             const bool relu = q.flags & FLAG_RELU;
             const bool pool = q.flags & FLAG_POOL;
             const bool f32 = q.flags & FLAG_F32;

@@ -201,12 +201,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int ep_tid = threadIdx.x - 64;           // 0..127
         int acc = 0;
         uint32_t acc_phase = 0;
+        int bias_loaded[kAccStages];
+#pragma unroll
+        for (int a = 0; a < kAccStages; ++a) bias_loaded[a] = -1;
         for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
             const TileCoord tc = decode_tile(p, t, BLOCK_N);
             const Prob& q = p.prob[tc.pi];
             float* bias_s = sbias + acc * BLOCK_N;
-            if (ep_tid < BLOCK_N) bias_s[ep_tid] = __ldg(q.bias + tc.n0 + ep_tid);
-            asm volatile("bar.sync 1, 128;" ::: "memory");           // bias visible to the 4 epilogue warps
+            // the bias slice changes only with the problem / n tile: reloading it for every tile put a global load and a
+            // barrier at the head of each epilogue, which is what paced the short-K (1x1, 3x3) layers
+            const int bias_key = (tc.pi << 16) | tc.n0;
+            if (bias_loaded[acc] != bias_key) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // nobody still reads this slot (two tiles back)
+                if (ep_tid < BLOCK_N) bias_s[ep_tid] = __ldg(q.bias + tc.n0 + ep_tid);
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // bias visible to the 4 epilogue warps
+                bias_loaded[acc] = bias_key;
+            }           // bias visible to the 4 epilogue warps
 
             const int tw_mask = (1 << q.tw_log2) - 1;
             const int tx = row & tw_mask, ty = row >> q.tw_log2;
