@@ -124,7 +124,9 @@ def test_hand_batch_equals_single():
         assert np.array_equal(batch[i], hand(crops[i]))
 
 
-@pytest.mark.parametrize("shape,scales", [((97, 131, 3), (0.5, 1.0)), ((61, 40, 3), (1.0,)), ((33, 200, 3), (0.5, 2.0))])
+@pytest.mark.parametrize("shape,scales", [((97, 131, 3), (0.5, 1.0)), ((61, 40, 3), (1.0,)), ((33, 200, 3), (0.5, 2.0)),
+                                          ((16, 16, 3), (0.5, 1.0)), ((9, 300, 3), (1.0,)), ((300, 9, 3), (0.5, 2.0)),
+                                          ((1080, 1920, 3), (0.5,))])
 def test_body_odd_sizes(shape, scales):
     """Ragged frames: widths not divisible by 4/8, maps smaller than a tile, very wide / very tall aspect ratios."""
     from pytorch_openpose_b200 import Body
