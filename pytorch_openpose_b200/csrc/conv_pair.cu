@@ -338,10 +338,9 @@ struct PairLaunch : ConvLaunch {
 
 template <int BN>
 void launch_pair(const PairLaunch& L, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) {
         OPB_CUDA(cudaFuncSetAttribute(conv_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, QCfg<BN>::kSmemBytes));
-        attr = true;
     }
     conv_pair_kernel<BN><<<L.grid, kThreads, QCfg<BN>::kSmemBytes, stream>>>(L.params);
 }

@@ -349,11 +349,10 @@ struct PatchLaunch : ConvLaunch {
 
 template <int BN, int MODE>
 void launch_one(const PatchLaunch& L, cudaStream_t stream) {
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) {
         OPB_CUDA(cudaFuncSetAttribute(conv_patch_kernel<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       PCfg<BN, MODE>::kSmemBytes));
-        attr = true;
     }
     conv_patch_kernel<BN, MODE><<<L.grid, kThreads, PCfg<BN, MODE>::kSmemBytes, stream>>>(L.params);
 }

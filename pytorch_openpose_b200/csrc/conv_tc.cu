@@ -414,13 +414,12 @@ static void conv_tc_prepare(const std::vector<ConvOp>& ops, int block_n, int num
 }
 
 static void conv_tc_run(const TapLaunch& L, cudaStream_t stream) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (first_use_on_device(attr_set)) {
         OPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg<128>::kSmemBytes));
         OPB_CUDA(cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       Cfg<64>::kSmemBytes));
-        attr_set = true;
     }
     if (L.block_n == 128)
         conv_tc_kernel<128><<<L.grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(L.params);

@@ -87,6 +87,17 @@ void conv_first_launch(const TensorView& in_u8, const TensorView& out, const flo
                        const float* bias, cudaStream_t stream);                    // conv1_1 (Cin=3) + ReLU
 void maxpool2_launch(const TensorView& in, const TensorView& out, cudaStream_t stream);
 
+// Function attributes (dynamic shared memory size) are per device: true the first time `flags` is consulted on the
+// current device (one flag array per kernel; contexts on several GPUs may live in one process).
+inline bool first_use_on_device(bool (&flags)[64]) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    dev &= 63;
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+
 // ---- pre/post processing (prepost.cu)
 void preprocess_launch(const uint8_t* img, int H, int W, uint8_t* out, int h, int w, int hp, int wp,
                        const int* x_first, const short* x_coef, const int* y_first, const short* y_coef,

@@ -296,10 +296,9 @@ void paf_group_launch2(const float* paf_planar, int H, int W, const double* cand
     OPB_CUDA(cudaGetLastError());
     limb_match_kernel<<<kLimbs, 256, 0, stream>>>(part_begin, lb, scratch_order, scratch_used, max_part);
     OPB_CUDA(cudaGetLastError());
-    static bool attr = false;
-    if (!attr) {
+    static bool attr[64] = {};
+    if (first_use_on_device(attr)) {
         OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
     }
     assemble_kernel<<<1, 32, (size_t)lb.subset_capacity * 20 * 8, stream>>>(candidates, lb);
     OPB_CUDA(cudaGetLastError());

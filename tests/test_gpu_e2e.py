@@ -260,3 +260,19 @@ def test_body_end_to_end_keypoints_within_1px(init, seed):
     print("%s: %d reference key points, %d device key points, %.1f %% within 1 px" % (init, n, len(cand), 100 * rate))
     # random-init maps have flat, noise-like maxima: a bf16 perturbation moves or merges some of them
     assert rate >= 0.8
+
+
+def test_two_devices_in_one_process():
+    """Contexts on two GPUs of one process (the library is normally used one process per GPU): same results."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from pytorch_openpose_b200 import Body, Hand
+    sd = O.make_weights("body", 1)
+    img = np.random.default_rng(5).integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    a = Body(sd, scale_search=[0.5, 1.0], device=0)(img)
+    b = Body(sd, scale_search=[0.5, 1.0], device=1)(img)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    sdh = O.make_weights("hand", 5, "kaiming")
+    crop = img[:96, :96]
+    assert np.array_equal(Hand(sdh, device=0)(crop), Hand(sdh, device=1)(crop))
