@@ -276,3 +276,40 @@ def test_two_devices_in_one_process():
     sdh = O.make_weights("hand", 5, "kaiming")
     crop = img[:96, :96]
     assert np.array_equal(Hand(sdh, device=0)(crop), Hand(sdh, device=1)(crop))
+
+
+def test_api_misuse_is_reported_not_crashed():
+    """Error codes of the C ABI for bad calls (include/openpose_b200.h conventions): no crash, no silent result."""
+    import ctypes
+    from pytorch_openpose_b200 import Body, Hand, _lib
+    body = Body(O.make_weights("body", 0))
+    hand = Hand(O.make_weights("hand", 0))
+    L = _lib.lib()
+    img = np.zeros((64, 64, 3), np.uint8)
+    sc, ns = _lib.scales_array([0.5])
+    # hand entry point on a body session and vice versa
+    assert L.opb_hand_submit(body._session.handle, img.ctypes.data, 0, 1, 64, 64, sc, ns) == _lib.OPB_ERR_INVALID
+    assert L.opb_body_submit(hand._session.handle, img.ctypes.data, 0, 64, 64, sc, ns) == _lib.OPB_ERR_INVALID
+    assert b"network" in L.opb_last_error()
+    # no scales, too many scales, too many frames, null image
+    assert L.opb_body_submit(body._session.handle, img.ctypes.data, 0, 64, 64, sc, 0) == _lib.OPB_ERR_INVALID
+    many, _ = _lib.scales_array([0.5] * 9)
+    assert L.opb_body_submit(body._session.handle, img.ctypes.data, 0, 64, 64, many, 9) == _lib.OPB_ERR_INVALID
+    assert L.opb_body_submit_batch(body._session.handle, img.ctypes.data, 0, 65, 64, 64, sc, ns) == _lib.OPB_ERR_INVALID
+    assert L.opb_body_submit(body._session.handle, None, 0, 64, 64, sc, ns) == _lib.OPB_ERR_INVALID
+    # waiting with nothing in flight
+    nc, nsub = ctypes.c_int(), ctypes.c_int()
+    fresh = body.net.session()
+    assert L.opb_body_wait(fresh.handle, ctypes.byref(nc), ctypes.byref(nsub)) == _lib.OPB_ERR_INVALID
+    # fetch buffers smaller than the result
+    frame = np.random.default_rng(0).integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    body.submit(frame)
+    assert L.opb_body_wait(body._session.handle, ctypes.byref(nc), ctypes.byref(nsub)) == _lib.OPB_OK and nc.value > 1
+    small = np.empty((1, 4))
+    assert L.opb_body_fetch(body._session.handle, small.ctypes.data, 1, None, 0) == _lib.OPB_ERR_CAPACITY
+    # ... and the session is still usable afterwards
+    cand, subset = body(frame)
+    assert len(cand) == nc.value
+    # Batch_hand sizes the reference cannot upsample by 8 are rejected by the library too
+    crop = np.zeros((1, 3, 100, 100), np.float32)
+    assert L.opb_batch_hand_submit(hand._session.handle, crop.ctypes.data, 0, 1, 100, 100) == _lib.OPB_ERR_INVALID
