@@ -381,6 +381,19 @@ def hand_crops_from_pose(image, pose, boxsize=368):
     return left, leftparams, right, rightparams
 
 
+def _box_to_roi(peaks, box, boxsize, mirrored):
+    """Key points of a `boxsize`-square hand image back to ROI coordinates (srcmx/Batch_motion_Estimation.py:41-56):
+    scale by w / boxsize, then shift by the box origin (and un-mirror x for left hands); coordinates that are exactly 0
+    mark missing key points and stay 0.  `box` = [x, y, w] (all zero when the hand was not found)."""
+    bx, by, bw = box
+    xy = peaks[:, :2] * bw / boxsize
+    px, py = xy[:, 0], xy[:, 1]
+    moved_x = (bw - px - 1 + bx) if mirrored else (px + bx)
+    peaks[:, 0] = np.where(px == 0, px, moved_x)
+    peaks[:, 1] = np.where(py == 0, py, py + by)
+    return peaks
+
+
 def batch_hand_extraction(videopath, motiondata, recpoints, outpath, batch_hand_estimation, boxsize=368, batchsize=32,
                           log=print):
     """`Batch_hand_extraction` (srcmx/Batch_motion_Estimation.py:19-63) -> HandMat (COUNTS, 42, 3): rows 0-20 left hand,
@@ -394,17 +407,9 @@ def batch_hand_extraction(videopath, motiondata, recpoints, outpath, batch_hand_
         items = [hand_crops_from_pose(frames[f], motiondata[first + f], boxsize) for f in range(len(frames))]
         lefts = batch_hand_estimation(to_tensor(np.stack([it[0] for it in items])))
         rights = batch_hand_estimation(to_tensor(np.stack([it[2] for it in items])))
-        for i, (_, (lx, ly, lw), _, (rx, ry, rw)) in enumerate(items):
-            rpeaks = rights[i]
-            rpeaks[:, :2] = rpeaks[:, :2] * rw / boxsize
-            rpeaks[:, 0] = np.where(rpeaks[:, 0] == 0, rpeaks[:, 0], rpeaks[:, 0] + rx)
-            rpeaks[:, 1] = np.where(rpeaks[:, 1] == 0, rpeaks[:, 1], rpeaks[:, 1] + ry)
-            mat[count, 21:, :] = rpeaks
-            lpeaks = lefts[i]
-            lpeaks[:, :2] = lpeaks[:, :2] * lw / boxsize
-            lpeaks[:, 0] = np.where(lpeaks[:, 0] == 0, lpeaks[:, 0], lw - lpeaks[:, 0] - 1 + lx)
-            lpeaks[:, 1] = np.where(lpeaks[:, 1] == 0, lpeaks[:, 1], lpeaks[:, 1] + ly)
-            mat[count, :21, :] = lpeaks
+        for i, (_, left_box, _, right_box) in enumerate(items):
+            mat[count, 21:, :] = _box_to_roi(rights[i], right_box, boxsize, mirrored=False)
+            mat[count, :21, :] = _box_to_roi(lefts[i], left_box, boxsize, mirrored=True)
             count += 1
             if count % 1000 == 0:
                 log("%s-%d/%d" % (outpath, count, len(motiondata)))
