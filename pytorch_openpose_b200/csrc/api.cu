@@ -429,8 +429,11 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     fp->launches_per_frame = n_scales /*preprocess*/ + fp->net->kernel_launches;
     if (body) {
         fp->post.resize(n);
+        // OPB_TEST_SMALL_BUFFERS: start with tiny result buffers so that tests exercise the growth path of body_wait
+        static const bool tiny = getenv("OPB_TEST_SMALL_BUFFERS") != nullptr;
         for (int f = 0; f < n; ++f)
-            alloc_body_post(fp->pool, fp->post[f], kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
+            alloc_body_post(fp->pool, fp->post[f], tiny ? 64 : kPeakCapacity, tiny ? 64 : kPairCapacity,
+                            tiny ? 16 : kConnCapacity, kSubsetCapacity);
         OPB_CUDA(cudaDeviceSynchronize());      // zero fills above ran on the legacy default stream
         fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/) + (mode >= 1);
     } else {
@@ -524,30 +527,73 @@ static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int
 
 // peaks -> grouping -> result copies for every frame of the batch.  mode 0: sigma-3 smoothing + NMS scored on the raw
 // map (src/body.py:70-94); mode 1: NMS on the 5x5-blurred map scored with the blurred value (utilmx.py:230-241).
-static void body_post_enqueue(opb_session* s, FramePlan* fp, int n, int H, int W) {
+static void body_post_frame(opb_session* s, FramePlan* fp, int f, int H, int W) {
     cudaStream_t st = s->stream;
     const size_t px = (size_t)H * W;
-    for (int f = 0; f < n; ++f) {
-        FramePlan::BodyPost& bp = fp->post[f];
-        if (fp->key.mode >= 1)
-            nms_f32_launch(fp->blurred + f * 19 * px, H, W, 18, 0.1f, bp.pb, st);                  // thre1, Batch_model.py:121
-        else
-            smooth_nms_launch(fp->heat_avg + f * 19 * px, H, W, 18, 0.1, bp.pb, nullptr, st);      // thre1, src/body.py:30
-        s->prof.mark(st, "smooth_nms");
-        sort_peaks_launch2(bp.pb, 18, bp.part_count, st);
-        s->prof.mark(st, "sort_peaks");
-        paf_group_launch2(fp->paf_avg + f * 38 * px, H, W, bp.pb.candidates, bp.pb.part_begin, bp.lb, 0.05, bp.order,
-                          bp.used, bp.pb.capacity, st);                                            // thre2, src/body.py:31
-        s->prof.mark(st, "paf_group");
-        HostResults* h = s->host + f;
-        OPB_CUDA(cudaMemcpyAsync(&h->counts[0], bp.pb.count, sizeof(int), cudaMemcpyDeviceToHost, st));
-        OPB_CUDA(cudaMemcpyAsync(&h->counts[1], bp.pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        OPB_CUDA(cudaMemcpyAsync(&h->counts[20], bp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-        OPB_CUDA(cudaMemcpyAsync(&h->counts[21], bp.lb.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-        OPB_CUDA(cudaMemcpyAsync(h->cand, bp.pb.candidates, sizeof(h->cand), cudaMemcpyDeviceToHost, st));
-        OPB_CUDA(cudaMemcpyAsync(h->subset, bp.lb.subset, sizeof(h->subset), cudaMemcpyDeviceToHost, st));
-        s->prof.mark(st, "d2h");
+    FramePlan::BodyPost& bp = fp->post[f];
+    if (fp->key.mode >= 1)
+        nms_f32_launch(fp->blurred + f * 19 * px, H, W, 18, 0.1f, bp.pb, st);                      // thre1, Batch_model.py:121
+    else
+        smooth_nms_launch(fp->heat_avg + f * 19 * px, H, W, 18, 0.1, bp.pb, nullptr, st);          // thre1, src/body.py:30
+    s->prof.mark(st, "smooth_nms");
+    sort_peaks_launch2(bp.pb, 18, bp.part_count, st);
+    s->prof.mark(st, "sort_peaks");
+    paf_group_launch2(fp->paf_avg + f * 38 * px, H, W, bp.pb.candidates, bp.pb.part_begin, bp.lb, 0.05, bp.order, bp.used,
+                      bp.pb.capacity, st);                                                         // thre2, src/body.py:31
+    s->prof.mark(st, "paf_group");
+    HostResults* h = s->host + f;
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[0], bp.pb.count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[1], bp.pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[20], bp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(&h->counts[21], bp.lb.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(h->cand, bp.pb.candidates, sizeof(double) * 4 * std::min(kEagerCand, bp.pb.capacity),
+                             cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaMemcpyAsync(h->subset, bp.lb.subset, sizeof(double) * 20 * std::min(kEagerSubset, bp.lb.subset_capacity),
+                             cudaMemcpyDeviceToHost, st));
+    s->prof.mark(st, "d2h");
+}
+
+static void body_post_enqueue(opb_session* s, FramePlan* fp, int n, int H, int W) {
+    for (int f = 0; f < n; ++f) body_post_frame(s, fp, f, H, W);
+}
+
+// A frame produced more peaks / scored limb pairs / connections than its buffers hold (the reference has no such limit):
+// give that frame larger buffers, repeat its post-processing on the maps that are still on the device, and make the
+// plan re-capture its graph.  Returns false when nothing can grow any further.
+static bool grow_and_redo(opb_session* s, FramePlan* fp, int f, int appended, int status) {
+    FramePlan::BodyPost& bp = fp->post[f];
+    int peak_cap = bp.pb.capacity, pair_cap = bp.lb.pair_capacity, conn_cap = bp.lb.conn_capacity;
+    const int subset_cap = bp.lb.subset_capacity;
+    constexpr int kMaxPeaks = 1 << 18, kMaxPairs = 1 << 18, kMaxConn = 1 << 15;
+    bool grew = false;
+    if (appended > peak_cap && peak_cap < kMaxPeaks) {
+        while (peak_cap < appended && peak_cap < kMaxPeaks) peak_cap *= 4;
+        grew = true;
     }
+    if ((status & kStPairOverflow) && pair_cap < kMaxPairs) {
+        pair_cap *= 4;
+        grew = true;
+    }
+    if ((status & kStConnOverflow) && conn_cap < kMaxConn) {
+        conn_cap *= 4;
+        grew = true;
+    }
+    if (!grew) return false;                             // kStSubsetOverflow: rows live in shared memory, fixed
+    OPB_CUDA(cudaStreamSynchronize(s->stream));
+    FramePlan::BodyPost bigger;
+    alloc_body_post(fp->pool, bigger, peak_cap, pair_cap, conn_cap, subset_cap);
+    OPB_CUDA(cudaDeviceSynchronize());                   // zero fills ran on the legacy default stream
+    bp = bigger;                                         // the old buffers stay in the plan's pool until it dies
+    if (fp->graph) {
+        cudaGraphExecDestroy(fp->graph);
+        fp->graph = nullptr;
+    }
+    const bool prof = s->prof.on;
+    s->prof.on = false;
+    body_post_frame(s, fp, f, fp->key.H, fp->key.W);
+    s->prof.on = prof;
+    OPB_CUDA(cudaStreamSynchronize(s->stream));
+    return true;
 }
 
 static void finish_submit(opb_session* s, FramePlan* fp) {
@@ -627,8 +673,14 @@ static int body_wait(opb_session* s, int* n_cand, int* n_subset, int* frame_stat
         HostResults* h = s->host + f;
         FramePlan::BodyPost& bp = fp->post[f];
         FrameResult& r = s->results[f];
-        const int appended = h->counts[0];
-        const int status = h->counts[21];
+        int appended = h->counts[0];
+        int status = h->counts[21];
+        for (int attempt = 0; attempt < 8; ++attempt) {
+            if (appended <= bp.pb.capacity && !(status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))) break;
+            if (!grow_and_redo(s, fp, f, appended, status)) break;
+            appended = h->counts[0];
+            status = h->counts[21];
+        }
         if (appended > bp.pb.capacity)
             throw Error(OPB_ERR_CAPACITY, "more than " + std::to_string(bp.pb.capacity) + " heat-map peaks in one frame");
         if (status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))

@@ -313,3 +313,43 @@ def test_api_misuse_is_reported_not_crashed():
     # Batch_hand sizes the reference cannot upsample by 8 are rejected by the library too
     crop = np.zeros((1, 3, 100, 100), np.float32)
     assert L.opb_batch_hand_submit(hand._session.handle, crop.ctypes.data, 0, 1, 100, 100) == _lib.OPB_ERR_INVALID
+
+
+def test_result_buffers_grow_instead_of_failing():
+    """The reference has no limit on peaks / limb pairs / connections per frame.  The device buffers are sized for
+    crowded frames and grow on demand; started tiny (OPB_TEST_SMALL_BUFFERS, own process) they must still give exactly
+    the reference post-processing's results, for single frames, batches and the batched estimator."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, cv2
+from oracle import openpose_oracle as O
+from oracle.make_golden import batch_frames
+from pytorch_openpose_b200 import Body, Batch_body
+sd = O.make_weights("body", 2, "kaiming")
+rng = np.random.default_rng(21)
+frames = np.stack([cv2.GaussianBlur(rng.integers(0, 256, (240, 320, 3), dtype=np.uint8), (0, 0), 3) for _ in range(3)])
+body = Body(sd, scale_search=[0.5, 1.0])
+for rep in range(4):                                  # eager, eager, captured graph, replay -- all after the growth
+    out = body.batch(frames)
+    heat, paf = body.last_maps(frames.shape)
+    for f in range(3):
+        rc, rs = O.body_postprocess(heat[f].astype(np.float64), paf[f].astype(np.float64), 240)
+        assert len(rc) > 64, len(rc)
+        assert np.array_equal(out[f][0], rc) and np.array_equal(out[f][1], rs)
+c, s = body(frames[0])
+assert np.array_equal(c, out[0][0]) and np.array_equal(s, out[0][1])
+est = Batch_body(sd)
+res = est(batch_frames(2, 240, 320, 42))
+blurred, paf = est.last_maps()
+for f in range(2):
+    rc, rs = O.batch_body_postprocess(blurred[f], paf[f])
+    assert len(rc) > 64
+    assert np.array_equal(np.asarray(res[f][0]).reshape(-1, 4), rc.reshape(-1, 4)) and np.array_equal(res[f][1], rs)
+print("GROWTH-OK")
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OPB_TEST_SMALL_BUFFERS="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert "GROWTH-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
