@@ -259,6 +259,42 @@ struct Builder {
             plan->kernel_launches += 1;
         }
     }
+    // Mconv6 + Mconv7 of a refinement stage as one fused launch (conv_tail.cu); OPB_NO_FUSE_TAILS=1: two grouped launches.
+    bool tail_group(const std::vector<std::string>& n6, const std::vector<std::string>& n7, const std::vector<TensorView>& ins,
+                    const std::vector<TensorView>& outs) {
+        static const bool fuse = getenv("OPB_NO_FUSE_TAILS") == nullptr;
+        if (!fuse) return false;
+        std::vector<TailOp> ops;
+        double gf = 0;
+        for (size_t i = 0; i < n6.size(); ++i) {
+            const DevLayer& a = net->dev.at(n6[i]);
+            const DevLayer& b = net->dev.at(n7[i]);
+            if (a.k != 1 || b.k != 1 || a.cin_dev != 128 || a.cout_pad != 128 || a.cout_store != 128 || !a.relu ||
+                b.cin_dev != 128 || b.cout_pad != 64)
+                return false;
+            TailOp op;
+            op.in = ins[i];
+            op.out = outs[i];
+            op.w1 = a.w; op.b1 = a.bias;
+            op.w2 = b.w; op.b2 = b.bias;
+            op.cout_pad2 = b.cout_pad;
+            op.cout_store = b.cout_store;
+            op.relu2 = b.relu;
+            ops.push_back(op);
+        }
+        if (!conv_tail_supported(ops)) return false;
+        for (size_t i = 0; i < n6.size(); ++i) {
+            gf += add_flops(n6[i], ins[i]);
+            gf += add_flops(n7[i], ins[i]);
+        }
+        ConvLaunch* L = conv_tail_plan(ops, net->ctx->num_sms);
+        plan->launches.push_back(L);
+        plan->steps.push_back([L](cudaStream_t s) { conv_tc_plan_run(L, s); });
+        plan->step_names.push_back("conv_tail:" + n6[0]);
+        plan->step_gflop.push_back(gf);
+        plan->kernel_launches += 1;
+        return true;
+    }
     // algorithmic FLOPs of one layer on one input (un-padded channel counts)
     double add_flops(const std::string& name, const TensorView& in) {
         for (const auto& s : layer_specs(net->kind))
@@ -429,8 +465,18 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
             branch_layer("Mconv3_stage%d_L%d", st, pb, pa, true);
             branch_layer("Mconv4_stage%d_L%d", st, pa, pb, true);
             branch_layer("Mconv5_stage%d_L%d", st, pb, pa, true);
-            branch_layer("Mconv6_stage%d_L%d", st, pa, pb, true);
-            branch_layer("Mconv7_stage%d_L%d", st, pb, slices(st == 6), true);
+            std::vector<std::string> n6(2 * S), n7(2 * S);
+            for (int s = 0; s < S; ++s)
+                for (int b = 0; b < 2; ++b) {
+                    snprintf(buf, sizeof buf, "Mconv6_stage%d_L%d", st, b + 1);
+                    n6[2 * s + b] = buf;
+                    snprintf(buf, sizeof buf, "Mconv7_stage%d_L%d", st, b + 1);
+                    n7[2 * s + b] = buf;
+                }
+            if (!B.tail_group(n6, n7, pa, slices(st == 6))) {
+                branch_layer("Mconv6_stage%d_L%d", st, pa, pb, true);
+                branch_layer("Mconv7_stage%d_L%d", st, pb, slices(st == 6), true);
+            }
         }
     } else {
         trunk("conv4_3", 512, false);
@@ -464,8 +510,11 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
             layer(nm(3), pb, pa);
             layer(nm(4), pa, pb);
             layer(nm(5), pb, pa);
-            layer(nm(6), pa, pb);
-            layer(nm(7), pb, st == 6 ? final_out : heat_slice);
+            if (!B.tail_group(std::vector<std::string>(S, nm(6)), std::vector<std::string>(S, nm(7)), pa,
+                              st == 6 ? final_out : heat_slice)) {
+                layer(nm(6), pa, pb);
+                layer(nm(7), pb, st == 6 ? final_out : heat_slice);
+            }
         }
     }
     return plan;

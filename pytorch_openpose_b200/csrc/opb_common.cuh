@@ -76,6 +76,16 @@ struct ConvLaunch {
 ConvLaunch* conv_tc_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms);               // per-tap tiles (any ks)
 ConvLaunch* conv_patch_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms, int mode);   // patch-resident (ks 3/7)
 ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_sms);              // CTA-pair cta_group::2 (ks 3/7)
+// fused 1x1 -> ReLU -> 1x1 tail of a refinement stage (conv_tail.cu): in 128 ch -> 128 ch -> cout_store (<= 64) channels
+struct TailOp {
+    TensorView in, out;
+    const __nv_bfloat16 *w1, *w2;   // [128][128] and [64][128], K-major
+    const float *b1, *b2;
+    int cout_pad2 = 64, cout_store = 0;
+    bool relu2 = false;             // ReLU after the second layer (the stage-6 L2 quirk of src/model.py:30-33)
+};
+bool conv_tail_supported(const std::vector<TailOp>& ops);
+ConvLaunch* conv_tail_plan(const std::vector<TailOp>& ops, int num_sms);
 inline void conv_tc_plan_run(const ConvLaunch* L, cudaStream_t stream) { L->run(stream); }
 inline void conv_tc_plan_free(ConvLaunch* L) { delete L; }
 void tensor_map_encode_bf16(CUtensorMap* tm, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
