@@ -257,7 +257,9 @@ def run_ours(args):
                 "traffic": traffic, "traffic_note": "DRAM bytes of the ncu-captured 7x7 stage launch (profiles/roofline_traffic.json)",
                 "gflop_per_launch": tc_gf / max(tc_n, 1), "ms_per_launch": tc_ms / max(tc_n, 1),
                 "gflop_per_frame": tc_gf / (n_prof * B), "ms_per_frame": tc_ms / (n_prof * B),
-                "measured_over": "%d serialised profiled batches of %d frames after the timed region (CUDA events around every launch)" % (n_prof, B)}
+                "measured_over": "%d serialised profiled batches of %d frames after the timed region (CUDA events around every launch)" % (n_prof, B),
+                "note": "peak is the driver's cuBLAS bf16 measurement (sustained, power-capped) for this pool; boxes differ by "
+                        "a few percent, so frac can land slightly above 1"}
 
     # ---- BASELINE.json's second metric: PAF-grouping ms/frame on the crowded synthetic scene (50 people) ----
     grouping = None
