@@ -145,6 +145,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     if world > 1:
         import torch.distributed as dist
+        # NCCL prints its version banner to STDOUT at NCCL_DEBUG=VERSION and WARN, which some images export: the contract
+        # is one JSON line on stdout, so NCCL logging is off unless the caller asks (OPB_NCCL_DEBUG=INFO shows NVLS etc.)
+        if "OPB_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["OPB_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
