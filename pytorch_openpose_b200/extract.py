@@ -471,3 +471,39 @@ def combine_motion_data(datafolder, outpath, mode, pattern=r"\d+"):
             out[key[0]] = (data[:, :18, :2].astype(np.int16), data[:, :18, -1].astype(np.float32))
     joblib.dump(out, outpath)
     return out
+
+
+# ---- the per-directory job loop (srcmx/Batch_motion_Estimation.py:143-163), one worker per GPU ----------------------
+VIDEO_EXTENSIONS = (".mp4", ".mkv", ".rmvb", ".avi")
+
+
+def run_body_job(videofolder, datadir, recpoint, process_video, mode="body", init=False, shuffle_seed=None, log=print):
+    """Every video of `videofolder` that nobody has claimed yet -> `datadir/video-XXX-<mode>.pkl` (XXX = first three
+    characters of the file name), exactly the loop of `Test(code=0)`: the output name is appended to the ledger BEFORE
+    the video is processed, and a name whose first nine characters are already in the ledger is skipped.  Several
+    workers (one process per GPU) may share `datadir`; the reference relies on shuffling to keep them apart, here a
+    claim is additionally made atomic with an exclusive lock file next to the ledger, so two workers never take the
+    same video.  `process_video(videopath, outpath)` does the work (e.g. a lambda around `batch_body_extraction`).
+    Returns the output names this worker produced."""
+    led = ExtractLedger(datadir)
+    if init or not os.path.exists(led.path):
+        led.files(init=True)
+    names = sorted(os.listdir(videofolder))
+    if shuffle_seed is not None:
+        np.random.default_rng(shuffle_seed).shuffle(names)
+    done = []
+    for filename in names:
+        if os.path.splitext(filename)[1] not in VIDEO_EXTENSIONS:
+            continue
+        outname = "video-%s-%s.pkl" % (filename[:3], mode)
+        if led.claimed(outname):
+            continue
+        try:                                            # atomic claim: only one worker creates the lock file
+            os.close(os.open(os.path.join(datadir, "." + outname[:9] + ".claim"), os.O_CREAT | os.O_EXCL | os.O_WRONLY))
+        except FileExistsError:
+            continue
+        log(outname)
+        led.add(outname)
+        process_video(os.path.join(videofolder, filename), os.path.join(datadir, outname))
+        done.append(outname)
+    return done

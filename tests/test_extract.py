@@ -211,3 +211,46 @@ def test_combined_dictionary_matches_reference(tmp_path):
             assert ref[k][0].dtype == mine[k][0].dtype == np.int16 and ref[k][1].dtype == mine[k][1].dtype == np.float32
             assert np.array_equal(ref[k][0], mine[k][0]) and np.array_equal(ref[k][1], mine[k][1])
     assert len(ref) == 0                           # the reference's bodyhand branch never stores anything
+
+
+def _job_worker(rank, videofolder, datadir, q):
+    import joblib
+
+    def process(videopath, outpath):
+        E.batch_body_extraction(videopath, outpath, 4, REC, lambda batch: [
+            fake_body(np.round(np.asarray(a).transpose(1, 2, 0) * 255).astype(np.uint8)) for a in batch], log=lambda m: None)
+
+    q.put((rank, E.run_body_job(videofolder, datadir, REC, process, shuffle_seed=rank, log=lambda m: None)))
+
+
+def test_two_workers_share_a_data_directory(video, tmp_path):
+    """One process per GPU, all pointing at the same data directory (srcmx/Batch_motion_Estimation.py:143-163): every
+    video is extracted exactly once, the ledger lists each output once, and a later run finds nothing left to do."""
+    import multiprocessing as mp
+    import shutil
+    import joblib
+    vids, data = tmp_path / "videos", tmp_path / "data"
+    vids.mkdir()
+    data.mkdir()
+    for k in range(5):
+        shutil.copy(video, str(vids / ("%03d-clip.avi" % k)))
+    (vids / "notes.txt").write_text("not a video")
+    E.ExtractLedger(str(data)).files(init=True)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_job_worker, args=(r, str(vids), str(data), q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = dict(q.get(timeout=300) for _ in ps)
+    for p in ps:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    produced = sorted(got[0] + got[1])
+    assert produced == ["video-%03d-body.pkl" % k for k in range(5)]              # disjoint and complete
+    ledger = [l.strip() for l in E.ExtractLedger(str(data)).files()]
+    assert sorted(ledger) == produced
+    ref = E.batch_body_extraction(video, str(tmp_path / "ref.pkl"), 4, REC, lambda batch: [
+        fake_body(np.round(np.asarray(a).transpose(1, 2, 0) * 255).astype(np.uint8)) for a in batch], log=lambda m: None)
+    for name in produced:
+        assert np.array_equal(joblib.load(str(data / name)), ref)
+    assert E.run_body_job(str(vids), str(data), REC, lambda a, b: 1 / 0, log=lambda m: None) == []   # nothing left
