@@ -7,10 +7,14 @@ import numpy as np
 
 def padRightDownCorner(img, stride, padValue):
     """Pad the bottom / right edges so both sides become multiples of `stride`.  Returns (padded, pad) with
-    pad = [up, left, down, right] (up and left are always 0)."""
+    pad = [up, left, down, right] (up and left are always 0).  Like the reference, which builds the pad rows from the
+    slice `[-2:-1]` (src/util.py:27,29), an image with a single row (column) gets NO bottom (right) padding although
+    `pad` still reports it."""
     h, w = img.shape[:2]
     pad = [0, 0, (stride - h % stride) % stride, (stride - w % stride) % stride]
-    out = np.full((h + pad[2], w + pad[3]) + img.shape[2:], padValue, dtype=img.dtype)
+    down = pad[2] if h > 1 else 0
+    right = pad[3] if w > 1 else 0
+    out = np.full((h + down, w + right) + img.shape[2:], padValue, dtype=img.dtype)
     out[:h, :w] = img
     return out, pad
 
