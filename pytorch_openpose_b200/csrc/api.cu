@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <cmath>
 
 namespace opb {
 
@@ -130,10 +131,13 @@ static F32Taps make_f32_taps(TableSlab& pool, int H, int W, const ScaleDims& d) 
 
 struct UpTables {
     int *xf, *yf;
-    float *xw, *yw;
-    int *ybf, *ybr;       // 16-row strip tables of the register-blocked y pass
+    float *xw, *yw;       // yw: 1/n_scales folded in
+    int *ybf, *ybr;       // 8-row strip tables of the register-blocked y pass
     float* ybw;
     int yb_rs;
+    // host copies / bounds for the fused peak kernel (peaks.cu)
+    std::vector<int> h_xf, h_ybf, h_ybr;
+    double l1 = 0, sum_min = 0, sum_max = 0;     // over all (y, x): sum |wy||wx| and range of (sum wy)(sum wx)
     void relocate_to(uint8_t* b) {
         relocate(xf, b); relocate(yf, b); relocate(xw, b); relocate(yw, b);
         relocate(ybf, b); relocate(ybr, b); relocate(ybw, b);
@@ -144,12 +148,14 @@ static UpTables make_up_tables(TableSlab& pool, int H, int W, const ScaleDims& d
     std::vector<float> wx, wy;
     composite_taps(d.wo, d.w, W, fx, wx);
     composite_taps(d.ho, d.h, H, fy, wy);
+    // the cross-scale average (heatmap / len(multiplier), src/body.py:67-68) is folded into the row weights
+    for (auto& v : wy) v = v / (float)n_scales;
     UpTables t;
     t.xf = pool.add(fx);
     t.yf = pool.add(fy);
     t.xw = pool.add(wx);
     t.yw = pool.add(wy);
-    // strips of 16 output rows: first source row, number of source rows, dense weights (x 1/n_scales)
+    // strips of 8 output rows: first source row, number of source rows, dense weights
     const int TY = kUpStrip, nyb = (H + TY - 1) / TY;
     std::vector<int> bf(nyb), br(nyb);
     int rs = 1;
@@ -168,12 +174,30 @@ static UpTables make_up_tables(TableSlab& pool, int H, int W, const ScaleDims& d
         for (int y = b * TY; y < std::min(H, (b + 1) * TY); ++y)
             for (int k = 0; k < kUpTaps; ++k) {
                 const int r = std::min(fy[y] + k, d.ho - 1) - bf[b];      // same clamp as the generic kernel
-                bw[((size_t)b * rs + r) * TY + (y - b * TY)] += wy[(size_t)y * kUpTaps + k] / (float)n_scales;
+                bw[((size_t)b * rs + r) * TY + (y - b * TY)] += wy[(size_t)y * kUpTaps + k];
             }
     t.ybf = pool.add(bf);
     t.ybr = pool.add(br);
     t.ybw = pool.add(bw);
     t.yb_rs = rs;
+    auto axis = [](const std::vector<float>& w, double& l1, double& smin, double& smax) {
+        l1 = 0; smin = 1e300; smax = -1e300;
+        for (size_t i = 0; i < w.size(); i += kUpTaps) {
+            double a = 0, sgn = 0;
+            for (int k = 0; k < kUpTaps; ++k) { a += std::fabs((double)w[i + k]); sgn += (double)w[i + k]; }
+            l1 = std::max(l1, a); smin = std::min(smin, sgn); smax = std::max(smax, sgn);
+        }
+    };
+    double l1x, l1y, sxl, sxh, syl, syh;
+    axis(wx, l1x, sxl, sxh);
+    axis(wy, l1y, syl, syh);
+    t.l1 = l1x * l1y;
+    const double c[4] = {sxl * syl, sxl * syh, sxh * syl, sxh * syh};
+    t.sum_min = *std::min_element(c, c + 4);
+    t.sum_max = *std::max_element(c, c + 4);
+    t.h_xf = fx;
+    t.h_ybf = bf;
+    t.h_ybr = br;
     return t;
 }
 
@@ -211,66 +235,69 @@ struct FramePlan {
     std::vector<UpTables> uptabs;
     NetPlan* net = nullptr;         // owned by the session's cache: shared by every frame size with the same net input
     TableSlab tables;               // host copy stays alive until the plan dies (source of an asynchronous copy)
+    bool fused_ok = false;          // tile footprints of the heat maps fit the fused peak kernel
     // bound from the session's arenas at every submit (one plan is in flight per session)
     uint8_t* d_img = nullptr;
+    // materialised full-resolution maps: hand crops always; body frames only when a caller asks for them
+    // (opb_body_maps / opb_batch_maps) or when the fused peak kernel does not fit the resize ratio
     float* up_scratch = nullptr;
-    float* heat_avg = nullptr;      // body: (19,H,W); hand: (n*22,H,W)
-    float* paf_avg = nullptr;       // body: (38,H,W)
+    float* heat_avg = nullptr;      // body: (n*19,H,W); hand: (n*22,H,W)
+    float* paf_avg = nullptr;       // body: (n*38,H,W)
     float* blurred = nullptr;       // batched estimators: 5x5-blurred heat maps, same shape as heat_avg
     size_t scratch_floats = 0;
-    // body post-processing, one set per frame of the batch
-    struct BodyPost {
-        PeakBuffers pb{};
-        int* part_count = nullptr;
-        LimbBuffers lb{};
-        int* order = nullptr;
-        unsigned char* used = nullptr;
-    };
-    std::vector<BodyPost> post;
+    // body post-processing: one FramePost per frame of the batch, a device copy of the table, one counter slab and
+    // one result slab for the whole batch
+    std::vector<FramePost> post;
+    FramePost* post_dev = nullptr;
+    int* counters = nullptr;        // [n][kCounterInts], cleared once per batch
+    unsigned* tile_mask = nullptr;  // [n][tiles] parts that can hold a peak, per tile of the peak kernel
+    FrameResults* results_dev = nullptr;
     // hand post-processing
     HandBuffers hb{};
     int launches_per_frame = 0;
 };
 
+constexpr int kCounterInts = 128;
 constexpr int kPeakCapacity = 16384;
 constexpr int kPairCapacity = 16384;
 constexpr int kConnCapacity = 2048;
-constexpr int kSubsetCapacity = 1024;
-constexpr int kEagerCand = 2048;      // rows copied to the host before the counts are known
-constexpr int kEagerSubset = 128;
+constexpr int kSubsetCapacity = kSubsetRowsShared;
 
-static void alloc_body_post(DevPool& pool, FramePlan::BodyPost& fp, int peak_cap, int pair_cap, int conn_cap, int subset_cap) {
+// counters: [0] peaks appended, [1] ordering ticket, [2..19] part counts, [20..38] part_begin, [40..58] survivors per
+// limb, [60..63] status, [64] subset rows, [65..83] connections per limb
+static void alloc_body_post(DevPool& pool, FramePost& fp, int* counters, FrameResults* result, int peak_cap, int pair_cap,
+                            int conn_cap, int subset_cap) {
     fp.pb.capacity = peak_cap;
     fp.pb.keys = pool.alloc_t<unsigned long long>(peak_cap);
     fp.pb.scores = pool.alloc_t<float>(peak_cap);
-    fp.pb.count = pool.alloc_t<int>(1, true);
+    fp.pb.count = counters + 0;
+    fp.pb.ticket = counters + 1;
+    fp.pb.part_count = counters + 2;
+    fp.pb.part_begin = counters + 20;
     fp.pb.candidates = pool.alloc_t<double>((size_t)peak_cap * 4, true);
-    fp.pb.part_begin = pool.alloc_t<int>(19, true);
-    fp.part_count = pool.alloc_t<int>(18, true);
     fp.lb.pair_capacity = pair_cap;
     fp.lb.conn_capacity = conn_cap;
     fp.lb.subset_capacity = subset_cap;
+    fp.lb.max_part = peak_cap;
     fp.lb.cand_score = pool.alloc_t<double>((size_t)19 * pair_cap);
     fp.lb.cand_ij = pool.alloc_t<int>((size_t)19 * pair_cap * 2);
-    fp.lb.cand_count = pool.alloc_t<int>(19, true);
+    fp.lb.cand_count = counters + 40;
+    fp.lb.status = counters + 60;
+    fp.lb.subset_count = counters + 64;
+    fp.lb.conn_count = counters + 65;
     fp.lb.conn = pool.alloc_t<double>((size_t)19 * conn_cap * 5, true);
-    fp.lb.conn_count = pool.alloc_t<int>(19, true);
     fp.lb.subset = pool.alloc_t<double>((size_t)subset_cap * 20, true);
-    fp.lb.subset_count = pool.alloc_t<int>(1, true);
-    fp.lb.status = pool.alloc_t<int>(4, true);
-    fp.order = pool.alloc_t<int>((size_t)19 * pair_cap);
-    fp.used = pool.alloc_t<unsigned char>((size_t)19 * 2 * peak_cap);
+    fp.lb.rows_global = subset_cap > kSubsetRowsShared ? pool.alloc_t<double>((size_t)subset_cap * 20) : nullptr;
+    fp.lb.order = pool.alloc_t<int>((size_t)19 * pair_cap);
+    fp.lb.used = pool.alloc_t<unsigned char>((size_t)19 * 2 * peak_cap);
+    fp.result = result;
 }
 
 }  // namespace opb
 
 using namespace opb;
 
-struct HostResults {                 // pinned, one per frame of a body batch
-    int counts[32];                  // [0] peaks appended, [1..19] part_begin, [20] subset rows, [21..24] status
-    double cand[kEagerCand * 4];
-    double subset[kEagerSubset * 20];
-};
+typedef FrameResults HostResults;    // pinned, one per frame of a body batch (same layout as the device block)
 struct FrameResult {                 // host-side view of one finished frame
     int n_cand = 0, n_subset = 0, status = 0;
     std::vector<double> cand_all, subset_all;   // filled by wait() when the eager copy was too small
@@ -294,7 +321,12 @@ struct opb_session {
     cudaEvent_t marks[2] = {nullptr, nullptr};
     // CNN plans keyed by the net input shapes only: every frame / crop size that resizes to the same shapes (all
     // square hand crops do: 184..736 squared, src/hand.py:38) shares one set of activations and tensor maps
-    std::map<std::vector<NetShape>, std::unique_ptr<NetPlan>> net_plans;
+    struct NetEntry {
+        std::unique_ptr<NetPlan> plan;
+        uint64_t last_use = 0;
+    };
+    std::map<std::vector<NetShape>, NetEntry> net_plans;
+    uint64_t use_clock = 0;
     // size-dependent work buffers, grown to the largest frame seen and shared by all plans of the session
     enum { AR_IMG, AR_SCRATCH, AR_HEAT, AR_PAF, AR_LABELS, AR_SUMS, AR_PEAKS, AR_BLUR, AR_COUNT };
     struct Arena { void* p = nullptr; size_t cap = 0; } arena[AR_COUNT];
@@ -340,24 +372,42 @@ static void ensure_staging(opb_session* s, size_t bytes) {
 constexpr size_t kMaxFramePlans = 512;     // tap tables only (tens of KB each)
 constexpr size_t kMaxNetPlans = 6;         // activations + tensor maps (hundreds of MB each)
 
-static void drop_plans(opb_session* s, bool nets_too) {
+static void drop_plans(opb_session* s) {
     OPB_CUDA(cudaStreamSynchronize(s->stream));
     s->plans.clear();
     s->active = nullptr;
-    if (nets_too) s->net_plans.clear();
 }
 
+// Plan construction allocates with cudaMalloc, uploads with synchronous copies and zero-fills through DevPool (which
+// waits for its own fill): nothing of it is ordered against, or waits for, the other sessions' streams.  When the
+// cache is full the least recently used CNN plan goes, together with the frame plans that point at it.
 static NetPlan* get_net_plan(opb_session* s, const std::vector<NetShape>& shapes) {
     auto it = s->net_plans.find(shapes);
-    if (it != s->net_plans.end()) return it->second.get();
-    if (s->net_plans.size() >= kMaxNetPlans) drop_plans(s, true);
-    OPB_CUDA(cudaDeviceSynchronize());          // no other session's work in flight while buffers are created
+    if (it != s->net_plans.end()) {
+        it->second.last_use = ++s->use_clock;
+        return it->second.plan.get();
+    }
+    if (s->net_plans.size() >= kMaxNetPlans) {
+        auto victim = s->net_plans.begin();
+        for (auto jt = s->net_plans.begin(); jt != s->net_plans.end(); ++jt)
+            if (jt->second.last_use < victim->second.last_use) victim = jt;
+        OPB_CUDA(cudaStreamSynchronize(s->stream));             // this session's work only
+        const NetPlan* dead = victim->second.plan.get();
+        for (auto pt = s->plans.begin(); pt != s->plans.end();) {
+            if (pt->second->net == dead) {
+                if (s->active == pt->second.get()) s->active = nullptr;
+                pt = s->plans.erase(pt);
+            } else {
+                ++pt;
+            }
+        }
+        s->net_plans.erase(victim);
+    }
     auto plan = build_net_plan(s->net, shapes);
-    // Plan construction uses cudaMalloc / cudaMemset / cudaMemcpy on the legacy default stream, which does NOT order
-    // with the sessions' non-blocking streams: finish it (zero fills included) before any kernel of the plan runs.
-    OPB_CUDA(cudaDeviceSynchronize());
     NetPlan* raw = plan.get();
-    s->net_plans[shapes] = std::move(plan);
+    auto& e = s->net_plans[shapes];
+    e.plan = std::move(plan);
+    e.last_use = ++s->use_clock;
     return raw;
 }
 
@@ -377,22 +427,34 @@ static void* arena_get(opb_session* s, int which, size_t bytes) {
 }
 
 // points the plan's work buffers at the session's arenas (which may have grown or moved since the last use)
+static void bind_maps(opb_session* s, FramePlan* fp, bool heat, bool paf, bool blurred) {
+    const size_t n = fp->key.n, px = (size_t)fp->key.H * fp->key.W;
+    const bool body = s->net->kind == OPB_NET_BODY;
+    fp->up_scratch = (float*)arena_get(s, opb_session::AR_SCRATCH, fp->scratch_floats * sizeof(float));
+    if (heat) fp->heat_avg = (float*)arena_get(s, opb_session::AR_HEAT, n * (body ? 19 : 22) * px * sizeof(float));
+    if (paf) fp->paf_avg = (float*)arena_get(s, opb_session::AR_PAF, n * 38 * px * sizeof(float));
+    if (blurred) fp->blurred = (float*)arena_get(s, opb_session::AR_BLUR, n * (body ? 19 : 22) * px * sizeof(float));
+}
+
 static void bind_buffers(opb_session* s, FramePlan* fp) {
     const size_t n = fp->key.n, px = (size_t)fp->key.H * fp->key.W;
     const bool body = s->net->kind == OPB_NET_BODY;
     const bool batch_mode = fp->key.mode >= 1;
     fp->d_img = (uint8_t*)arena_get(s, opb_session::AR_IMG, n * px * 3 * (fp->key.mode == 1 ? sizeof(float) : 1));
-    if (batch_mode) fp->blurred = (float*)arena_get(s, opb_session::AR_BLUR, n * (body ? 19 : 22) * px * sizeof(float));
-    fp->up_scratch = (float*)arena_get(s, opb_session::AR_SCRATCH, fp->scratch_floats * sizeof(float));
     if (body) {
-        fp->heat_avg = (float*)arena_get(s, opb_session::AR_HEAT, n * 19 * px * sizeof(float));
-        fp->paf_avg = (float*)arena_get(s, opb_session::AR_PAF, n * 38 * px * sizeof(float));
+        // the full-resolution maps are not materialised (peaks.cu / paf.cu evaluate them on the fly) unless the
+        // resize ratio is outside what the fused kernel's shared memory holds
+        if (!fp->fused_ok) bind_maps(s, fp, true, false, false);
     } else {
-        fp->heat_avg = (float*)arena_get(s, opb_session::AR_HEAT, n * 22 * px * sizeof(float));
+        bind_maps(s, fp, true, false, batch_mode);
         fp->hb.labels = (int*)arena_get(s, opb_session::AR_LABELS, n * 21 * px * sizeof(int));
         fp->hb.sums = (double*)arena_get(s, opb_session::AR_SUMS, n * 21 * px * sizeof(double));
         fp->hb.peaks = (double*)arena_get(s, opb_session::AR_PEAKS, n * 21 * 3 * sizeof(double));
     }
+}
+
+static void upload_post_table(FramePlan* fp, cudaStream_t st) {
+    OPB_CUDA(cudaMemcpyAsync(fp->post_dev, fp->post.data(), fp->post.size() * sizeof(FramePost), cudaMemcpyHostToDevice, st));
 }
 
 static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* scales, int n_scales, int mode = 0) {
@@ -400,11 +462,14 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     FrameKey key{n, H, W, std::vector<double>(scales, scales + n_scales), mode};
     auto it = s->plans.find(key);
     if (it != s->plans.end()) {
-        bind_buffers(s, it->second.get());
-        return it->second.get();
+        FramePlan* fp = it->second.get();
+        auto nt = s->net_plans.find(fp->net->shapes);
+        if (nt != s->net_plans.end()) nt->second.last_use = ++s->use_clock;
+        bind_buffers(s, fp);
+        return fp;
     }
     OPB_CUDA(cudaSetDevice(s->net->ctx->device));
-    if (s->plans.size() >= kMaxFramePlans) drop_plans(s, false);
+    if (s->plans.size() >= kMaxFramePlans) drop_plans(s);
     auto fp = std::make_unique<FramePlan>();
     fp->key = key;
     const bool body = s->net->kind == OPB_NET_BODY;
@@ -419,7 +484,7 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
         shapes.push_back({n, d.hp, d.wp, mode >= 1 ? 2 : 1});
         fp->scratch_floats += (size_t)n * C * d.ho * W;
     }
-    fp->net = get_net_plan(s, shapes);          // may drop every cached plan of the session (not this one: not inserted yet)
+    fp->net = get_net_plan(s, shapes);          // may evict another CNN plan of the session (and its frame plans)
     // tables: one device allocation, one copy ordered on the session's stream (no device-wide synchronisation, so a
     // new crop size on one session does not stall the others)
     uint8_t* dev_tables = commit_tables(fp->pool, fp->tables, s->stream);
@@ -428,14 +493,30 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
     for (auto& t : fp->uptabs) t.relocate_to(dev_tables);
     fp->launches_per_frame = n_scales /*preprocess*/ + fp->net->kernel_launches;
     if (body) {
-        fp->post.resize(n);
+        std::vector<std::vector<int>> xf, ybf, ybr;
+        std::vector<int> wo, rs;
+        for (int i = 0; i < n_scales; ++i) {
+            xf.push_back(fp->uptabs[i].h_xf);
+            ybf.push_back(fp->uptabs[i].h_ybf);
+            ybr.push_back(fp->uptabs[i].h_ybr);
+            wo.push_back(fp->dims[i].wo);
+            rs.push_back(fp->uptabs[i].yb_rs);
+        }
+        static const bool no_fuse = getenv("OPB_NO_FUSED_PEAKS") != nullptr;      // A/B switch: materialised planes
+        fp->fused_ok = !no_fuse && composite_fits_fused(xf, ybf, ybr, wo, rs, H, W);
         // OPB_TEST_SMALL_BUFFERS: start with tiny result buffers so that tests exercise the growth path of body_wait
         static const bool tiny = getenv("OPB_TEST_SMALL_BUFFERS") != nullptr;
+        fp->counters = fp->pool.alloc_t<int>((size_t)n * kCounterInts, true);
+        fp->results_dev = fp->pool.alloc_t<FrameResults>(n, true);
+        fp->post_dev = fp->pool.alloc_t<FramePost>(n);
+        fp->tile_mask = fp->pool.alloc_t<unsigned>(find_peaks_mask_words(n, H, W));
+        fp->post.resize(n);
         for (int f = 0; f < n; ++f)
-            alloc_body_post(fp->pool, fp->post[f], tiny ? 64 : kPeakCapacity, tiny ? 64 : kPairCapacity,
-                            tiny ? 16 : kConnCapacity, kSubsetCapacity);
-        OPB_CUDA(cudaDeviceSynchronize());      // zero fills above ran on the legacy default stream
-        fp->launches_per_frame += 2 * (n_scales + 1) /*upsample*/ + n * (1 /*nms*/ + 2 /*sort*/ + 3 /*paf*/) + (mode >= 1);
+            alloc_body_post(fp->pool, fp->post[f], fp->counters + (size_t)f * kCounterInts, fp->results_dev + f,
+                            tiny ? 64 : kPeakCapacity, tiny ? 64 : kPairCapacity, tiny ? 16 : kConnCapacity,
+                            tiny ? 4 : kSubsetCapacity);
+        upload_post_table(fp.get(), s->stream);
+        fp->launches_per_frame += 7 + (fp->fused_ok ? 0 : n_scales + 1);
     } else {
         fp->launches_per_frame += (n_scales + 1) + 6 + (mode >= 1);
     }
@@ -446,7 +527,7 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
 }
 
 // Runs `enqueue` (kernel launches, memsets and result copies on the session's stream) either directly or, once the plan
-// has been used a few times, as one CUDA graph launch: a frame is ~110 small dependent launches, and for the small
+// has been used a few times, as one CUDA graph launch: a frame is ~70 small dependent launches, and for the small
 // default configuration (640x480, one scale) the launch gaps, not the kernels, are most of the latency.
 template <typename F>
 static void run_or_replay(opb_session* s, FramePlan* fp, F&& enqueue) {
@@ -505,6 +586,7 @@ static void run_front(opb_session* s, FramePlan* fp, int n, int H, int W) {
     fp->net->run(st, s->prof.on ? &s->prof : nullptr);
 }
 
+// materialises the averaged full-resolution maps (hand crops; body maps on request)
 static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int H, int W, float* out, cudaStream_t st) {
     UpsampleScale us[kMaxScales];
     const int S = (int)fp->dims.size();
@@ -525,46 +607,74 @@ static void run_upsample(FramePlan* fp, bool paf, int n, int C, int cstride, int
     upsample_avg_launch2(us, S, n, C, H, W, fp->up_scratch, out, st);
 }
 
-// peaks -> grouping -> result copies for every frame of the batch.  mode 0: sigma-3 smoothing + NMS scored on the raw
-// map (src/body.py:70-94); mode 1: NMS on the 5x5-blurred map scored with the blurred value (utilmx.py:230-241).
-static void body_post_frame(opb_session* s, FramePlan* fp, int f, int H, int W) {
+// the averaged map as a function of the net outputs (peaks.cu, paf.cu evaluate it where they need it)
+static CompositeMap composite_of(const FramePlan* fp, bool paf, int cstride) {
+    CompositeMap m;
+    memset(&m, 0, sizeof(m));
+    const int S = (int)fp->dims.size();
+    m.n_scales = S;
+    for (int i = 0; i < S; ++i) {
+        CompositeScale& c = m.sc[i];
+        const UpTables& t = fp->uptabs[i];
+        c.src = paf ? fp->net->out_paf[i] : fp->net->out_heat[i];
+        c.ho = fp->dims[i].ho;
+        c.wo = fp->dims[i].wo;
+        c.cstride = cstride;
+        c.frame_stride = (size_t)c.ho * c.wo * cstride;
+        c.xf = t.xf; c.xw = t.xw; c.yf = t.yf; c.yw = t.yw;
+        c.ybf = t.ybf; c.ybr = t.ybr; c.ybw = t.ybw; c.yb_rs = t.yb_rs;
+        c.l1 = (float)(t.l1 * 1.00001);
+        c.sum_min = (float)(t.sum_min - 1e-5 * std::fabs(t.sum_min));
+        c.sum_max = (float)(t.sum_max + 1e-5 * std::fabs(t.sum_max));
+    }
+    m.fused_ok = fp->fused_ok;
+    return m;
+}
+
+// peaks -> grouping -> result copy for frames [f0, f0 + nf) of the batch.  mode 0: sigma-3 smoothing + NMS scored on
+// the raw map (src/body.py:70-94); mode 1: NMS on the 5x5-blurred map scored with the blurred value (utilmx.py:230-241).
+static void body_post_range(opb_session* s, FramePlan* fp, int f0, int nf, int H, int W) {
     cudaStream_t st = s->stream;
-    const size_t px = (size_t)H * W;
-    FramePlan::BodyPost& bp = fp->post[f];
-    if (fp->key.mode >= 1)
-        nms_f32_launch(fp->blurred + f * 19 * px, H, W, 18, 0.1f, bp.pb, st);                      // thre1, Batch_model.py:121
-    else
-        smooth_nms_launch(fp->heat_avg + f * 19 * px, H, W, 18, 0.1, bp.pb, nullptr, st);          // thre1, src/body.py:30
-    s->prof.mark(st, "smooth_nms");
-    sort_peaks_launch2(bp.pb, 18, bp.part_count, st);
-    s->prof.mark(st, "sort_peaks");
-    paf_group_launch2(fp->paf_avg + f * 38 * px, H, W, bp.pb.candidates, bp.pb.part_begin, bp.lb, 0.05, bp.order, bp.used,
-                      bp.pb.capacity, st);                                                         // thre2, src/body.py:31
+    const int mode = fp->key.mode >= 1 ? 1 : 0;
+    OPB_CUDA(cudaMemsetAsync(fp->counters + (size_t)f0 * kCounterInts, 0, (size_t)nf * kCounterInts * sizeof(int), st));
+    MapSource heat, paf;
+    heat.frame_base = paf.frame_base = f0;
+    if (fp->fused_ok) {
+        heat.comp = composite_of(fp, false, 24);
+    } else {
+        if (f0 == 0) run_upsample(fp, false, fp->key.n, 19, 24, H, W, fp->heat_avg, st);
+        heat.planar = fp->heat_avg;
+        heat.planes_per_frame = 19;
+    }
+    paf.comp = composite_of(fp, true, 40);
+    int peak_cap = 0, subset_cap = 0;
+    for (int f = f0; f < f0 + nf; ++f) {
+        peak_cap = std::max(peak_cap, fp->post[f].pb.capacity);
+        subset_cap = std::max(subset_cap, fp->post[f].lb.subset_capacity);
+    }
+    find_peaks_launch(heat, nf, H, W, 18, mode, 0.1, fp->post_dev + f0, nullptr, fp->tile_mask, st);      // thre1: src/body.py:30, Batch_model.py:121
+    s->prof.mark(st, "find_peaks");
+    order_peaks_launch(fp->post_dev + f0, nf, peak_cap, 18, st);
+    s->prof.mark(st, "order_peaks");
+    paf_group_launch(paf, nf, H, W, fp->post_dev + f0, 0.05, subset_cap, st);               // thre2, src/body.py:31
     s->prof.mark(st, "paf_group");
-    HostResults* h = s->host + f;
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[0], bp.pb.count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[1], bp.pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[20], bp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(&h->counts[21], bp.lb.status, 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(h->cand, bp.pb.candidates, sizeof(double) * 4 * std::min(kEagerCand, bp.pb.capacity),
-                             cudaMemcpyDeviceToHost, st));
-    OPB_CUDA(cudaMemcpyAsync(h->subset, bp.lb.subset, sizeof(double) * 20 * std::min(kEagerSubset, bp.lb.subset_capacity),
-                             cudaMemcpyDeviceToHost, st));
+    pack_results_launch(fp->post_dev + f0, nf, st);
+    OPB_CUDA(cudaMemcpyAsync(s->host + f0, fp->results_dev + f0, (size_t)nf * sizeof(FrameResults), cudaMemcpyDeviceToHost, st));
     s->prof.mark(st, "d2h");
 }
 
 static void body_post_enqueue(opb_session* s, FramePlan* fp, int n, int H, int W) {
-    for (int f = 0; f < n; ++f) body_post_frame(s, fp, f, H, W);
+    body_post_range(s, fp, 0, n, H, W);
 }
 
-// A frame produced more peaks / scored limb pairs / connections than its buffers hold (the reference has no such limit):
-// give that frame larger buffers, repeat its post-processing on the maps that are still on the device, and make the
-// plan re-capture its graph.  Returns false when nothing can grow any further.
+// A frame produced more peaks / scored limb pairs / connections / person rows than its buffers hold (the reference has
+// no such limits): give that frame larger buffers, repeat its post-processing from the net outputs that are still on
+// the device, and make the plan re-capture its graph.  Returns false when nothing can grow any further.
 static bool grow_and_redo(opb_session* s, FramePlan* fp, int f, int appended, int status) {
-    FramePlan::BodyPost& bp = fp->post[f];
+    FramePost& bp = fp->post[f];
     int peak_cap = bp.pb.capacity, pair_cap = bp.lb.pair_capacity, conn_cap = bp.lb.conn_capacity;
-    const int subset_cap = bp.lb.subset_capacity;
-    constexpr int kMaxPeaks = 1 << 18, kMaxPairs = 1 << 18, kMaxConn = 1 << 15;
+    int subset_cap = bp.lb.subset_capacity;
+    constexpr int kMaxPeaks = 1 << 18, kMaxPairs = 1 << 20, kMaxConn = 1 << 16, kMaxSubset = 1 << 16;
     bool grew = false;
     if (appended > peak_cap && peak_cap < kMaxPeaks) {
         while (peak_cap < appended && peak_cap < kMaxPeaks) peak_cap *= 4;
@@ -578,19 +688,24 @@ static bool grow_and_redo(opb_session* s, FramePlan* fp, int f, int appended, in
         conn_cap *= 4;
         grew = true;
     }
-    if (!grew) return false;                             // kStSubsetOverflow: rows live in shared memory, fixed
+    if ((status & kStSubsetOverflow) && subset_cap < kMaxSubset) {        // beyond 1024 rows: global work rows
+        subset_cap *= 4;
+        grew = true;
+    }
+    if (!grew) return false;
     OPB_CUDA(cudaStreamSynchronize(s->stream));
-    FramePlan::BodyPost bigger;
-    alloc_body_post(fp->pool, bigger, peak_cap, pair_cap, conn_cap, subset_cap);
-    OPB_CUDA(cudaDeviceSynchronize());                   // zero fills ran on the legacy default stream
+    FramePost bigger;
+    alloc_body_post(fp->pool, bigger, fp->counters + (size_t)f * kCounterInts, fp->results_dev + f, peak_cap, pair_cap,
+                    conn_cap, subset_cap);
     bp = bigger;                                         // the old buffers stay in the plan's pool until it dies
+    upload_post_table(fp, s->stream);
     if (fp->graph) {
         cudaGraphExecDestroy(fp->graph);
         fp->graph = nullptr;
     }
     const bool prof = s->prof.on;
     s->prof.on = false;
-    body_post_frame(s, fp, f, fp->key.H, fp->key.W);
+    body_post_range(s, fp, f, 1, fp->key.H, fp->key.W);
     s->prof.on = prof;
     OPB_CUDA(cudaStreamSynchronize(s->stream));
     return true;
@@ -616,9 +731,6 @@ static void body_submit(opb_session* s, const uint8_t* img, int where, int n, in
     s->prof.mark(st, "h2d");
     run_or_replay(s, fp, [&] {
         run_front(s, fp, n, H, W);
-        run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
-        run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
-        s->prof.mark(st, "upsample_avg");
         body_post_enqueue(s, fp, n, H, W);
     });
     finish_submit(s, fp);
@@ -651,12 +763,7 @@ static void batch_body_submit(opb_session* s, const void* frames, bool u8, int w
     s->prof.mark(st, "h2d");
     run_or_replay(s, fp, [&] {
         run_front_f32(s, fp, n, H, W);
-        run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, st);
-        run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, st);
-        s->prof.mark(st, "upsample_avg");
-        blur5_launch(fp->heat_avg, fp->blurred, n * 19, H, W, st);                                 // utilmx.py:261-263
-        s->prof.mark(st, "blur5");
-        body_post_enqueue(s, fp, n, H, W);
+        body_post_enqueue(s, fp, n, H, W);              // 5x5 blur (utilmx.py:261-263) inside the peak kernel
     });
     finish_submit(s, fp);
 }
@@ -671,11 +778,11 @@ static int body_wait(opb_session* s, int* n_cand, int* n_subset, int* frame_stat
     bool extra = false;
     for (int f = 0; f < s->n_frames; ++f) {
         HostResults* h = s->host + f;
-        FramePlan::BodyPost& bp = fp->post[f];
+        FramePost& bp = fp->post[f];
         FrameResult& r = s->results[f];
         int appended = h->counts[0];
         int status = h->counts[21];
-        for (int attempt = 0; attempt < 8; ++attempt) {
+        for (int attempt = 0; attempt < 12; ++attempt) {
             if (appended <= bp.pb.capacity && !(status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))) break;
             if (!grow_and_redo(s, fp, f, appended, status)) break;
             appended = h->counts[0];
@@ -769,7 +876,7 @@ static void batch_hand_submit(opb_session* s, const void* crops, bool u8, int wh
         run_front_f32(s, fp, n, H, W);
         run_upsample(fp, false, n, 22, 24, H, W, fp->heat_avg, st);                                // x8 bicubic, :377
         s->prof.mark(st, "upsample_avg");
-        blur5_launch(fp->heat_avg, fp->blurred, n * 22, H, W, st);                                 // :378
+        blur5_planar_launch(fp->heat_avg, fp->blurred, n * 22, H, W, st);                                 // :378
         s->prof.mark(st, "blur5");
         hand_peaks_blurred_launch(fp->blurred, n, 22, H, W, 0.035f, fp->hb, st);                   // thre, :361
         s->prof.mark(st, "hand_peaks");
@@ -978,10 +1085,23 @@ int opb_session_elapsed(opb_session* a, int slot_a, opb_session* b, int slot_b, 
 int opb_body_maps(opb_session* s, float* host_heat, float* host_paf) {
     return guarded([&] {
         OPB_REQUIRE(s && s->active && s->net->kind == OPB_NET_BODY, "no finished body frame");
+        OPB_CUDA(cudaSetDevice(s->net->ctx->device));
         OPB_CUDA(cudaEventSynchronize(s->done));
-        const size_t px = (size_t)s->active->key.H * s->active->key.W * s->active->key.n;     // all frames of a batch
-        if (host_heat) OPB_CUDA(cudaMemcpy(host_heat, s->active->heat_avg, px * 19 * 4, cudaMemcpyDeviceToHost));
-        if (host_paf) OPB_CUDA(cudaMemcpy(host_paf, s->active->paf_avg, px * 38 * 4, cudaMemcpyDeviceToHost));
+        // The frame path never writes the full-resolution maps (peaks.cu / paf.cu evaluate them where needed); they are
+        // materialised here, from the net outputs still held by the plan, with the same per-element arithmetic.
+        FramePlan* fp = s->active;
+        const int n = fp->key.n, H = fp->key.H, W = fp->key.W;
+        const size_t px = (size_t)H * W * n;                                                   // all frames of a batch
+        bind_maps(s, fp, host_heat != nullptr, host_paf != nullptr, false);
+        if (host_heat) {
+            run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, s->stream);
+            OPB_CUDA(cudaMemcpyAsync(host_heat, fp->heat_avg, px * 19 * 4, cudaMemcpyDeviceToHost, s->stream));
+        }
+        if (host_paf) {
+            run_upsample(fp, true, n, 38, 40, H, W, fp->paf_avg, s->stream);
+            OPB_CUDA(cudaMemcpyAsync(host_paf, fp->paf_avg, px * 38 * 4, cudaMemcpyDeviceToHost, s->stream));
+        }
+        OPB_CUDA(cudaStreamSynchronize(s->stream));
     });
 }
 int opb_hand_maps(opb_session* s, float* host_heat) {
@@ -1020,10 +1140,19 @@ int opb_batch_hand_submit_u8(opb_session* s, const uint8_t* crops, int where, in
 int opb_batch_maps(opb_session* s, float* host_blurred_heat) {
     return guarded([&] {
         OPB_REQUIRE(s && s->active && s->active->key.mode >= 1 && host_blurred_heat, "no finished batched-estimator call");
+        OPB_CUDA(cudaSetDevice(s->net->ctx->device));
         OPB_CUDA(cudaEventSynchronize(s->done));
-        const size_t px = (size_t)s->active->key.H * s->active->key.W * s->active->key.n;
+        FramePlan* fp = s->active;
+        const int n = fp->key.n, H = fp->key.H, W = fp->key.W;
+        const size_t px = (size_t)H * W * n;
         const int C = s->net->kind == OPB_NET_BODY ? 19 : 22;
-        OPB_CUDA(cudaMemcpy(host_blurred_heat, s->active->blurred, px * C * 4, cudaMemcpyDeviceToHost));
+        if (s->net->kind == OPB_NET_BODY) {              // body frames: materialised on request only (see opb_body_maps)
+            bind_maps(s, fp, true, false, true);
+            run_upsample(fp, false, n, 19, 24, H, W, fp->heat_avg, s->stream);
+            blur5_planar_launch(fp->heat_avg, fp->blurred, n * 19, H, W, s->stream);
+        }
+        OPB_CUDA(cudaMemcpyAsync(host_blurred_heat, fp->blurred, px * C * 4, cudaMemcpyDeviceToHost, s->stream));
+        OPB_CUDA(cudaStreamSynchronize(s->stream));
     });
 }
 
@@ -1116,71 +1245,62 @@ int opb_upsample_avg(opb_context* ctx, const float* const* dev_maps, const doubl
     });
 }
 
+// one frame's post-processing buffers for the stage-level entry points
+struct StagePost {
+    DevPool pool;
+    FramePost host;
+    FramePost* dev = nullptr;
+    int* counters = nullptr;
+    void create(int peak_cap, int pair_cap, int conn_cap, int subset_cap, double* ext_candidates, cudaStream_t st) {
+        counters = pool.alloc_t<int>(kCounterInts, true);
+        alloc_body_post(pool, host, counters, nullptr, peak_cap, pair_cap, conn_cap, subset_cap);
+        if (ext_candidates) host.pb.candidates = ext_candidates;
+        dev = pool.alloc_t<FramePost>(1);
+        OPB_CUDA(cudaMemcpyAsync(dev, &host, sizeof(FramePost), cudaMemcpyHostToDevice, st));
+    }
+    void clear(cudaStream_t st) { OPB_CUDA(cudaMemsetAsync(counters, 0, kCounterInts * sizeof(int), st)); }
+};
+
+static void stage_find_peaks(opb_context* ctx, const float* dev_map, int H, int W, int mode, double thre1,
+                             double* dev_candidates, int capacity, int* host_part_begin19, int* n) {
+    OPB_REQUIRE(capacity > 0 && dev_candidates && host_part_begin19 && n, "bad arguments");
+    OPB_CUDA(cudaSetDevice(ctx->device));
+    StagePost sp;
+    sp.create(capacity, 1, 1, 1, dev_candidates, ctx->stream);
+    MapSource src;
+    src.planar = dev_map;
+    src.planes_per_frame = 18;
+    find_peaks_launch(src, 1, H, W, 18, mode, thre1, sp.dev, nullptr, nullptr, ctx->stream);
+    order_peaks_launch(sp.dev, 1, capacity, 18, ctx->stream);
+    ctx->launches += 2;
+    int appended = 0;
+    OPB_CUDA(cudaMemcpyAsync(&appended, sp.host.pb.count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    OPB_CUDA(cudaMemcpyAsync(host_part_begin19, sp.host.pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n = appended;
+    if (appended > capacity) throw Error(OPB_ERR_CAPACITY, "peak buffer too small");
+}
+
 int opb_find_peaks(opb_context* ctx, const float* dev_heat, int H, int W, double thre1, double* dev_candidates,
                    int capacity, int* host_part_begin19, int* n) {
-    return guarded([&] {
-        OPB_REQUIRE(capacity > 0 && dev_candidates && host_part_begin19 && n, "bad arguments");
-        OPB_CUDA(cudaSetDevice(ctx->device));
-        DevPool pool;
-        PeakBuffers pb;
-        pb.capacity = capacity;
-        pb.keys = pool.alloc_t<unsigned long long>(capacity);
-        pb.scores = pool.alloc_t<float>(capacity);
-        pb.count = pool.alloc_t<int>(1, true);
-        pb.candidates = dev_candidates;
-        pb.part_begin = pool.alloc_t<int>(19, true);
-        int* part_count = pool.alloc_t<int>(18, true);
-        smooth_nms_launch(dev_heat, H, W, 18, thre1, pb, nullptr, ctx->stream);
-        sort_peaks_launch2(pb, 18, part_count, ctx->stream);
-        ctx->launches += 3;
-        int appended = 0;
-        OPB_CUDA(cudaMemcpyAsync(&appended, pb.count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        OPB_CUDA(cudaMemcpyAsync(host_part_begin19, pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
-        *n = appended;
-        if (appended > capacity) throw Error(OPB_ERR_CAPACITY, "peak buffer too small");
-    });
+    return guarded([&] { stage_find_peaks(ctx, dev_heat, H, W, 0, thre1, dev_candidates, capacity, host_part_begin19, n); });
 }
 
 int opb_find_peaks_blurred(opb_context* ctx, const float* dev_blurred, int H, int W, double thre1, double* dev_candidates,
                            int capacity, int* host_part_begin19, int* n) {
-    return guarded([&] {
-        OPB_REQUIRE(capacity > 0 && dev_candidates && host_part_begin19 && n, "bad arguments");
-        OPB_CUDA(cudaSetDevice(ctx->device));
-        DevPool pool;
-        PeakBuffers pb;
-        pb.capacity = capacity;
-        pb.keys = pool.alloc_t<unsigned long long>(capacity);
-        pb.scores = pool.alloc_t<float>(capacity);
-        pb.count = pool.alloc_t<int>(1, true);
-        pb.candidates = dev_candidates;
-        pb.part_begin = pool.alloc_t<int>(19, true);
-        int* part_count = pool.alloc_t<int>(18, true);
-        OPB_CUDA(cudaDeviceSynchronize());
-        nms_f32_launch(dev_blurred, H, W, 18, (float)thre1, pb, ctx->stream);
-        sort_peaks_launch2(pb, 18, part_count, ctx->stream);
-        ctx->launches += 3;
-        int appended = 0;
-        OPB_CUDA(cudaMemcpyAsync(&appended, pb.count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        OPB_CUDA(cudaMemcpyAsync(host_part_begin19, pb.part_begin, 19 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
-        *n = appended;
-        if (appended > capacity) throw Error(OPB_ERR_CAPACITY, "peak buffer too small");
-    });
+    return guarded([&] { stage_find_peaks(ctx, dev_blurred, H, W, 2, thre1, dev_candidates, capacity, host_part_begin19, n); });
 }
 
 int opb_smooth_debug(opb_context* ctx, const float* dev_heat, int parts, int H, int W, double* dev_smoothed) {
     return guarded([&] {
+        OPB_REQUIRE(dev_heat && dev_smoothed && parts >= 1, "bad arguments");
         OPB_CUDA(cudaSetDevice(ctx->device));
-        DevPool pool;
-        PeakBuffers pb;
-        pb.capacity = 1;
-        pb.keys = pool.alloc_t<unsigned long long>(1);
-        pb.scores = pool.alloc_t<float>(1);
-        pb.count = pool.alloc_t<int>(1, true);
-        pb.candidates = pool.alloc_t<double>(4);
-        pb.part_begin = pool.alloc_t<int>(19, true);
-        smooth_nms_launch(dev_heat, H, W, parts, 1e300, pb, dev_smoothed, ctx->stream);
+        StagePost sp;
+        sp.create(1, 1, 1, 1, nullptr, ctx->stream);
+        MapSource src;
+        src.planar = dev_heat;
+        src.planes_per_frame = parts;
+        find_peaks_launch(src, 1, H, W, parts, 0, 1e300, sp.dev, dev_smoothed, nullptr, ctx->stream);
         OPB_CUDA(cudaStreamSynchronize(ctx->stream));
     });
 }
@@ -1192,29 +1312,31 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int H, int W, const 
     int g = guarded([&] {
         OPB_REQUIRE(dev_paf && dev_candidates && host_part_begin19 && host_subset && n_subset, "null argument");
         OPB_CUDA(cudaSetDevice(ctx->device));
-        DevPool pool;
-        FramePlan::BodyPost fp;
         const int total = host_part_begin19[18];
         int max_part = 1;
         for (int p = 0; p < 18; ++p) max_part = std::max(max_part, host_part_begin19[p + 1] - host_part_begin19[p]);
         const int conn_cap = conn_capacity > 0 ? conn_capacity : std::max(1, max_part);
-        alloc_body_post(pool, fp, std::max(total, 1), kPairCapacity, conn_cap, std::min(std::max(subset_capacity, 1), 1280));
-        OPB_CUDA(cudaMemcpy(fp.pb.part_begin, host_part_begin19, 19 * sizeof(int), cudaMemcpyHostToDevice));
-        paf_group_launch2(dev_paf, H, W, dev_candidates, fp.pb.part_begin, fp.lb, thre2, fp.order, fp.used,
-                          std::max(total, 1), ctx->stream);
+        StagePost sp;
+        sp.create(std::max(total, 1), kPairCapacity, conn_cap, std::max(subset_capacity, 1), const_cast<double*>(dev_candidates),
+                  ctx->stream);
+        OPB_CUDA(cudaMemcpyAsync(sp.host.pb.part_begin, host_part_begin19, 19 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        MapSource src;
+        src.planar = dev_paf;
+        src.planes_per_frame = 38;
+        paf_group_launch(src, 1, H, W, sp.dev, thre2, sp.host.lb.subset_capacity, ctx->stream);
         ctx->launches += 3;
         int status[4], count = 0;
-        OPB_CUDA(cudaMemcpyAsync(status, fp.lb.status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
-        OPB_CUDA(cudaMemcpyAsync(&count, fp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaMemcpyAsync(status, sp.host.lb.status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaMemcpyAsync(&count, sp.host.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
         OPB_CUDA(cudaStreamSynchronize(ctx->stream));
         if (status[0] & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))
             throw Error(OPB_ERR_CAPACITY, "limb / person buffers overflowed (status " + std::to_string(status[0]) + ")");
         *n_subset = count;
         if (count > subset_capacity) throw Error(OPB_ERR_CAPACITY, "subset buffer too small");
-        if (count) OPB_CUDA(cudaMemcpy(host_subset, fp.lb.subset, (size_t)count * 20 * 8, cudaMemcpyDeviceToHost));
+        if (count) OPB_CUDA(cudaMemcpy(host_subset, sp.host.lb.subset, (size_t)count * 20 * 8, cudaMemcpyDeviceToHost));
         if (host_connections && host_conn_count19) {
-            OPB_CUDA(cudaMemcpy(host_conn_count19, fp.lb.conn_count, 19 * sizeof(int), cudaMemcpyDeviceToHost));
-            OPB_CUDA(cudaMemcpy(host_connections, fp.lb.conn, (size_t)19 * conn_cap * 5 * 8, cudaMemcpyDeviceToHost));
+            OPB_CUDA(cudaMemcpy(host_conn_count19, sp.host.lb.conn_count, 19 * sizeof(int), cudaMemcpyDeviceToHost));
+            OPB_CUDA(cudaMemcpy(host_connections, sp.host.lb.conn, (size_t)19 * conn_cap * 5 * 8, cudaMemcpyDeviceToHost));
         }
         if (status[0] & kStIndexError) {
             set_last_error("list assignment index out of range (src/body.py:173)");
@@ -1229,17 +1351,21 @@ int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev
     return guarded([&] {
         OPB_REQUIRE(dev_heat && dev_paf && ms_per_frame && iters >= 1, "bad arguments");
         OPB_CUDA(cudaSetDevice(ctx->device));
-        DevPool pool;
-        FramePlan::BodyPost bp;
-        alloc_body_post(pool, bp, kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity);
+        StagePost sp;
+        sp.create(kPeakCapacity, kPairCapacity, kConnCapacity, kSubsetCapacity, nullptr, ctx->stream);
+        MapSource heat, paf;
+        heat.planar = dev_heat;
+        heat.planes_per_frame = 19;
+        paf.planar = dev_paf;
+        paf.planes_per_frame = 38;
         cudaEvent_t e0, e1;
         OPB_CUDA(cudaEventCreate(&e0));
         OPB_CUDA(cudaEventCreate(&e1));
         auto once = [&] {
-            smooth_nms_launch(dev_heat, H, W, 18, 0.1, bp.pb, nullptr, ctx->stream);
-            sort_peaks_launch2(bp.pb, 18, bp.part_count, ctx->stream);
-            paf_group_launch2(dev_paf, H, W, bp.pb.candidates, bp.pb.part_begin, bp.lb, 0.05, bp.order, bp.used,
-                              bp.pb.capacity, ctx->stream);
+            sp.clear(ctx->stream);
+            find_peaks_launch(heat, 1, H, W, 18, 0, 0.1, sp.dev, nullptr, nullptr, ctx->stream);
+            order_peaks_launch(sp.dev, 1, sp.host.pb.capacity, 18, ctx->stream);
+            paf_group_launch(paf, 1, H, W, sp.dev, 0.05, sp.host.lb.subset_capacity, ctx->stream);
         };
         for (int i = 0; i < 3; ++i) once();
         OPB_CUDA(cudaEventRecord(e0, ctx->stream));
@@ -1249,10 +1375,10 @@ int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev
         float ms = 0.f;
         OPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         *ms_per_frame = ms / (float)iters;
-        ctx->launches += 6 * (iters + 3);
+        ctx->launches += 5 * (iters + 3);
         int pb19[19], ns = 0;
-        OPB_CUDA(cudaMemcpy(pb19, bp.pb.part_begin, sizeof(pb19), cudaMemcpyDeviceToHost));
-        OPB_CUDA(cudaMemcpy(&ns, bp.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost));
+        OPB_CUDA(cudaMemcpy(pb19, sp.host.pb.part_begin, sizeof(pb19), cudaMemcpyDeviceToHost));
+        OPB_CUDA(cudaMemcpy(&ns, sp.host.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost));
         if (n_candidate) *n_candidate = pb19[18];
         if (n_subset) *n_subset = ns;
         cudaEventDestroy(e0);

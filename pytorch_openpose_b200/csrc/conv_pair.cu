@@ -13,6 +13,7 @@
 //                     epilogue (own TMEM rows), which releases the accumulator by arriving on the LEADER's barrier.
 #include "opb_common.cuh"
 #include "tc_ptx.cuh"
+#include <cstdlib>
 
 namespace opb {
 namespace {
@@ -35,6 +36,8 @@ struct QProb {
     int out_cstride, cout_store;
     int n_tiles_n, cin_chunks;
     int pair_begin, flags;
+    int vsplit;                  // 0: the two 128-pixel halves of a super-tile sit side by side (8 cols x 16 rows each),
+                                 // 1: stacked (16 cols x 8 rows each) -- chosen per problem for the least padding
 };
 
 struct alignas(64) PairParams {
@@ -73,6 +76,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 struct TileCoord {
     int pi, img, x0, y0, n0;
     bool real;                   // false: padding tile of an odd problem (computed, never stored)
+    int halves;                  // bit h: half h of the super-tile holds at least one pixel of the image
 };
 __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, int rank, int block_n) {
     int pi = 0;
@@ -88,13 +92,21 @@ __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, in
     const int per_img = q.tiles_x * q.tiles_y;
     const int img = mt / per_img;
     const int r = mt - img * per_img;
-    const int tyi = r / q.tiles_x;
-    const int txi = r - tyi * q.tiles_x;
+    int txi, tyi;
+    if (q.vsplit) {              // row-major: the two tiles of a pair are horizontal neighbours (same rows -> same empty half)
+        tyi = r / q.tiles_x;
+        txi = r - tyi * q.tiles_x;
+    } else {                     // column-major: vertical neighbours (same columns)
+        txi = r / q.tiles_y;
+        tyi = r - txi * q.tiles_y;
+    }
     c.pi = pi;
     c.img = img;
     c.x0 = txi * kTile;
     c.y0 = tyi * kTile;
     c.n0 = nt * block_n;
+    const bool second = q.vsplit ? (c.y0 + 8 < q.H) : (c.x0 + 8 < q.W);
+    c.halves = c.real ? (second ? 3 : 1) : 0;
     return c;
 }
 
@@ -201,6 +213,10 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
             for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
                 const TileCoord tc = decode_pair(p, pr, 0, BLOCK_N);
                 const QProb& q = p.prob[tc.pi];
+                // a half that is outside the image in BOTH tiles of the pair is neither multiplied nor stored
+                const int halves = tc.halves | decode_pair(p, pr, 1, BLOCK_N).halves;
+                const uint32_t half_off = q.vsplit ? 8u * kPitch * 128u : 8u * 128u;
+                const uint32_t sbo = q.vsplit ? 1024u : (uint32_t)(kPitch * 128);
                 uint32_t accum[kHalves] = {0, 0};
                 mbar_wait(&tempty[acc], acc_phase ^ 1, 12);               // both epilogues drained this accumulator
                 tc_fence_after();
@@ -216,7 +232,8 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                             const uint64_t bdesc = make_desc(smem_u32(bstages + bs * C::kBHalfBytes), 1024);
 #pragma unroll
                             for (int h = 0; h < kHalves; ++h) {
-                                const uint64_t adesc = make_desc(patch_addr + (uint32_t)((dy * kPitch + h * 8) * 128), kPitch * 128);
+                                if (!(halves & (1 << h))) continue;
+                                const uint64_t adesc = make_desc(patch_addr + (uint32_t)(dy * kPitch * 128) + h * half_off, sbo);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
                                     umma_bf16_2sm_elect(d_tmem + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, accum[h]);
@@ -239,7 +256,6 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
         const int quad = warp & 3;
         const int row = quad * 32 + lane;
         const int ep_tid = threadIdx.x - 64;
-        const int tx = row & 7, ty = row >> 3;
         int acc = 0;
         uint32_t acc_phase = 0;
         int bias_loaded[kAccStages];
@@ -262,14 +278,19 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
             const bool pool = q.flags & FLAG_POOL;
             const bool f32 = q.flags & FLAG_F32;
             const int n_valid = q.cout_store - tc.n0;
-            const int y = tc.y0 + ty;
+            const bool vsplit = q.vsplit != 0;
+            // pixel of accumulator row `row` inside the half: 8 x 16 (side by side) or 16 x 8 (stacked)
+            const int tx = vsplit ? (row & 15) : (row & 7);
+            const int ty = vsplit ? (row >> 4) : (row >> 3);
+            const int pool_dy = vsplit ? 16 : 8;                      // lane distance of the row below
 
             mbar_wait(&tfull[acc], acc_phase, 15);
             tc_fence_after();
 #pragma unroll 1
             for (int h = 0; h < kHalves; ++h) {
-                if (!tc.real || tc.x0 + 8 * h >= q.W) break;
-                const int x = tc.x0 + 8 * h + tx;
+                if (!(tc.halves & (1 << h))) break;
+                const int x = tc.x0 + (vsplit ? 0 : 8 * h) + tx;
+                const int y = tc.y0 + (vsplit ? 8 * h : 0) + ty;
                 const bool inside = (x < q.W) && (y < q.H);
                 size_t pix;
                 bool writer;
@@ -297,7 +318,7 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
                             const float m = fmaxf(f[j], __shfl_xor_sync(0xffffffffu, f[j], 1));
-                            f[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+                            f[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, pool_dy));
                         }
                     }
                     if (writer) {
@@ -394,6 +415,13 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         q.cin_chunks = op.in.c / 64;
         q.pair_begin = pairs;
         q.flags = (op.relu ? FLAG_RELU : 0) | (op.out.elem == 4 ? FLAG_F32 : 0) | (op.pool ? FLAG_POOL : 0);
+        {
+            // 128-pixel halves actually multiplied: side by side -> columns round up to 8 and rows to 16; stacked ->
+            // columns to 16 and rows to 8 (e.g. 41x23: 48x32 vs 48x24; 82x46: 88x48 vs 96x48)
+            static const char* force = getenv("OPB_PAIR_SPLIT");
+            const long side = (long)cdiv(W, 8) * 8 * cdiv(H, 16) * 16, stacked = (long)cdiv(W, 16) * 16 * cdiv(H, 8) * 8;
+            q.vsplit = force ? atoi(force) : (stacked < side ? 1 : 0);
+        }
         pairs += q.m_pairs * q.n_tiles_n;
 
         cuuint64_t adims[4] = {(cuuint64_t)op.in.c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};

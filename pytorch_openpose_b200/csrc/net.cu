@@ -97,7 +97,13 @@ void* DevPool::alloc(size_t n, bool zero) {
     OPB_CUDA(cudaMalloc(&p, n));
     ptrs.push_back(p);
     bytes += n;
-    if (zero) OPB_CUDA(cudaMemset(p, 0, n));
+    if (zero) {
+        // The fill runs on the legacy default stream, which the library's non-blocking streams do not order against:
+        // wait for it here (this stream only -- no device-wide synchronisation), so that no kernel launched afterwards
+        // on any stream can be overtaken by it.
+        OPB_CUDA(cudaMemsetAsync(p, 0, n, cudaStreamLegacy));
+        OPB_CUDA(cudaStreamSynchronize(cudaStreamLegacy));
+    }
     return p;
 }
 void DevPool::release() {

@@ -120,7 +120,6 @@ void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t*
 void preprocess_f32_launch(const void* frames, bool frames_u8_hwc, int n, int H, int W, void* out_bf16, int h, int w,
                            int hp, int wp, const int* x_first, const float* x_w, const int* y_first, const float* y_w,
                            cudaStream_t stream);
-void blur5_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream);
 
 constexpr int kUpStrip = 8;          // output rows per register-blocked strip of the y upsample pass (tables + kernel)
 struct UpsampleScale {
@@ -129,7 +128,7 @@ struct UpsampleScale {
     const int* x_first;       // [W]    first source column of the composite footprint
     const float* x_w;         // [W][6] composite weights
     const int* y_first;       // [H]
-    const float* y_w;         // [H][6]
+    const float* y_w;         // [H][6], 1/n_scales folded in
     // optional 16-row strip tables for the register-blocked y pass (null -> generic kernel)
     const int* yb_first = nullptr;     // [ceil(H/16)]
     const int* yb_rows = nullptr;      // [ceil(H/16)]
@@ -141,6 +140,33 @@ constexpr int kMaxScales = 8;
 void upsample_avg_launch2(const UpsampleScale* scales, int n_scales, int n_img, int C, int H, int W, float* scratch,
                           float* out_planar, cudaStream_t stream);
 
+// ---- composite map: the averaged full-resolution map of src/body.py:54-68 as a FUNCTION of the low-resolution
+// net outputs (composite.cuh).  value(ch, y, x) = chain over scales s, taps k of fmaf(yw_s[y][k], t_s(min(yf_s[y]+k,
+// ho-1), x), .) with t_s(r, x) = chain over j of fmaf(xw_s[x][j], src_s[r][min(xf_s[x]+j, wo-1)][ch], .) -- the same
+// per-element arithmetic as the materialising kernels of prepost.cu, so a value sampled on demand is bit-identical
+// to the plane opb_body_maps returns.
+struct CompositeScale {
+    const float* src;         // fp32 NHWC net output, frame 0
+    size_t frame_stride;      // elements between frames
+    int ho, wo, cstride;
+    const int* xf;            // [W]     first source column
+    const float* xw;          // [W][6]
+    const int* yf;            // [H]
+    const float* yw;          // [H][6]  1/n_scales folded in
+    const int* ybf;           // [ceil(H/8)]           strip tables of the register-blocked y pass
+    const int* ybr;           // [ceil(H/8)]
+    const float* ybw;         // [ceil(H/8)][yb_rs][8]
+    int yb_rs;
+    // bounds over all output positions (host, float64, rounded outwards): sum of |weights| and range of the sum of
+    // weights -- this scale's contribution is <= mid * sum + l1 * halfwidth for inputs in [mid - halfwidth, mid + halfwidth]
+    float l1, sum_min, sum_max;
+};
+struct CompositeMap {
+    CompositeScale sc[kMaxScales];
+    int n_scales = 0;
+    bool fused_ok = false;    // tile footprints fit the fused kernel's shared-memory budget (peaks.cu)
+};
+
 // ---- peaks (peaks.cu)
 struct PeakBuffers {
     unsigned long long* keys;   // [capacity] unordered (part<<40 | y<<20 | x)
@@ -148,12 +174,10 @@ struct PeakBuffers {
     int* count;                 // [1] number appended (may exceed capacity -> overflow)
     double* candidates;         // [capacity][4] sorted (x, y, score, id)
     int* part_begin;            // [19] prefix offsets per part (18 parts + total)
+    int* part_count;            // [18] scratch of the ordering kernel
+    int* ticket;                // [1]  scratch of the ordering kernel (last-block-done counter)
     int capacity;
 };
-void smooth_nms_launch(const float* heat_planar, int H, int W, int parts, double thre, PeakBuffers pb,
-                       double* smoothed_out /* optional [parts][H][W] or null */, cudaStream_t stream);
-void sort_peaks_launch2(PeakBuffers pb, int parts, int* part_count_scratch, cudaStream_t stream);
-void nms_f32_launch(const float* blurred_planar, int H, int W, int parts, float thre, PeakBuffers pb, cudaStream_t stream);
 
 // ---- PAF grouping (paf.cu)
 struct LimbBuffers {
@@ -163,14 +187,60 @@ struct LimbBuffers {
     double* conn;             // [19][conn_capacity][5]  (idA, idB, score, i, j)
     int* conn_count;          // [19]
     double* subset;           // [subset_capacity][20]
+    double* rows_global;      // [subset_capacity][20] assembly work rows when they do not fit shared memory, else null
     int* subset_count;        // [1] rows after pruning
     int* status;              // [4]: bit flags (overflow / IndexError edge), rows before pruning, ...
-    int pair_capacity, conn_capacity, subset_capacity;
+    int* order;               // [19][pair_capacity] sorted order of the survivors
+    unsigned char* used;      // [19][2][max_part]
+    int pair_capacity, conn_capacity, subset_capacity, max_part;
 };
-void paf_group_launch2(const float* paf_planar, int H, int W, const double* candidates, const int* part_begin,
-                       LimbBuffers lb, double thre2, int* scratch_order, unsigned char* scratch_used, int max_part,
-                       cudaStream_t stream);
 constexpr int kStPairOverflow = 1, kStConnOverflow = 2, kStSubsetOverflow = 4, kStIndexError = 8;
+constexpr int kSubsetRowsShared = 1024;   // assembly rows kept in shared memory up to this many
+
+// everything the post-processing kernels need for ONE frame of a batch; the kernels take a device array of these
+// and pick theirs by block index, so a batch is one launch per stage
+constexpr int kEagerCand = 2048;      // rows copied to the host before the counts are known
+constexpr int kEagerSubset = 128;
+struct FrameResults {                // device mirror of the pinned host block, one per frame
+    int counts[32];                  // [0] peaks appended, [1..19] part_begin, [20] subset rows, [21..24] status
+    double cand[kEagerCand * 4];
+    double subset[kEagerSubset * 20];
+};
+struct FramePost {
+    PeakBuffers pb;
+    LimbBuffers lb;
+    FrameResults* result;     // may be null (stage-level entry points)
+};
+
+// where the heat / PAF values come from: materialised planes, or the composite map evaluated on the fly
+struct MapSource {
+    const float* planar = nullptr;    // (frames * planes_per_frame, H, W) fp32 or null
+    int planes_per_frame = 0;
+    int frame_base = 0;               // frame index of the first FramePost of the launch (partial re-runs of a batch)
+    CompositeMap comp;                // used when planar == null
+};
+
+// peak finding over `parts` maps of every frame.  mode 0: sigma-3 Gaussian in scipy's float64 arithmetic, peaks
+// scored with the raw value (src/body.py:70-94); mode 1: 5x5 blur in float32, fixed tap order, peaks found and
+// scored on the blurred value (srcmx/utilmx.py:230-263); mode 2: mode 1 on a plane that already holds the blurred map.
+// Ordered candidates + part_begin are written by
+// order_peaks_launch.
+// tile_mask_scratch: device words, find_peaks_mask_words(n_frames, H, W) of them (composite sources only).
+void find_peaks_launch(const MapSource& src, int n_frames, int H, int W, int parts, int mode, double thre,
+                       const FramePost* frames_dev, double* smoothed_out /* mode 0 debug, single frame */,
+                       unsigned* tile_mask_scratch, cudaStream_t stream);
+size_t find_peaks_mask_words(int n_frames, int H, int W);
+// do all tile footprints of a composite map fit the fused kernel's shared-memory budget? (host tables per scale)
+bool composite_fits_fused(const std::vector<std::vector<int>>& xf, const std::vector<std::vector<int>>& ybf,
+                          const std::vector<std::vector<int>>& ybr, const std::vector<int>& wo, const std::vector<int>& yb_rs,
+                          int H, int W);
+void order_peaks_launch(const FramePost* frames_dev, int n_frames, int max_capacity, int parts, cudaStream_t stream);
+void blur5_planar_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream);
+
+void paf_group_launch(const MapSource& paf, int n_frames, int H, int W, const FramePost* frames_dev, double thre2,
+                      int subset_capacity, cudaStream_t stream);
+// copies counts + the first rows of candidates / subsets of every frame into FramePost::result
+void pack_results_launch(const FramePost* frames_dev, int n_frames, cudaStream_t stream);
 
 // ---- hand peaks (hand.cu)
 struct HandBuffers {

@@ -10,8 +10,14 @@
 //   limb_match_kernel one CTA per limb: rank-sorts survivors by (score desc, i asc, j asc) == Python's stable
 //                     sorted(..., reverse=True) over the (i, j) loop order, then walks them greedily.
 //   assemble_kernel   one warp: the reference's sequential row merge (found==1 / found==2 / new row, k < 17),
-//                     rows kept in shared memory, row search parallel over lanes, then pruning.
-#include "opb_common.cuh"
+//                     rows kept in shared memory (in a global work buffer beyond 1024 rows), row search parallel
+//                     over lanes, then pruning.
+// The PAF values come either from materialised planes or straight from the low-resolution net outputs
+// (composite.cuh: the same fmaf chains as the materialising kernels, so the samples are bit-identical to the planes
+// opb_body_maps returns) -- a frame needs 10 samples per candidate pair, not 38 full-resolution planes.
+// Every kernel handles all frames of a batch: the frame is a grid dimension.
+#include "composite.cuh"
+#include <algorithm>
 
 namespace opb {
 namespace {
@@ -24,11 +30,15 @@ __constant__ int c_paf_x[kLimbs] = {12, 20, 14, 16, 22, 24, 0, 2, 4, 6, 8, 10, 2
 
 constexpr int ST_PAIR_OVERFLOW = 1, ST_CONN_OVERFLOW = 2, ST_SUBSET_OVERFLOW = 4, ST_INDEX_ERROR = 8;
 
-__global__ void __launch_bounds__(256) paf_score_kernel(const float* __restrict__ paf, int H, int W,
-                                                        const double* __restrict__ cand,
-                                                        const int* __restrict__ part_begin, LimbBuffers lb,
-                                                        double thre2) {
+template <bool PLANAR>
+__global__ void __launch_bounds__(256) paf_score_kernel(const __grid_constant__ MapSource src, int H, int W,
+                                                        const FramePost* __restrict__ frames, double thre2) {
     const int k = blockIdx.y;
+    const int frame = blockIdx.z;
+    const FramePost& fr = frames[frame];
+    const double* __restrict__ cand = fr.pb.candidates;
+    const int* __restrict__ part_begin = fr.pb.part_begin;
+    const LimbBuffers& lb = fr.lb;
     const int pa = c_limb_a[k], pb = c_limb_b[k];
     const int a0 = part_begin[pa], nA = part_begin[pa + 1] - a0;
     const int b0 = part_begin[pb], nB = part_begin[pb + 1] - b0;
@@ -36,8 +46,12 @@ __global__ void __launch_bounds__(256) paf_score_kernel(const float* __restrict_
     const int lane = threadIdx.x & 31;
     const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-    const float* px_map = paf + (size_t)c_paf_x[k] * H * W;
-    const float* py_map = px_map + (size_t)H * W;
+    const float* px_map = nullptr;
+    const float* py_map = nullptr;
+    if (PLANAR) {
+        px_map = src.planar + ((size_t)(frame + src.frame_base) * src.planes_per_frame + c_paf_x[k]) * H * W;
+        py_map = px_map + (size_t)H * W;
+    }
 
     for (long long pr = warp0; pr < pairs; pr += nwarps) {
         const int i = (int)(pr / nB), j = (int)(pr - (long long)i * nB);
@@ -58,8 +72,15 @@ __global__ void __launch_bounds__(256) paf_score_kernel(const float* __restrict_
                 sy = __dadd_rn(__dmul_rn((double)lane, vy / 9.0), ay);
             }
             const int xi = (int)rint(sx), yi = (int)rint(sy);                  // int(round()): half to even
-            const double fx = (double)px_map[(size_t)yi * W + xi];
-            const double fy = (double)py_map[(size_t)yi * W + xi];
+            double fx, fy;
+            if (PLANAR) {
+                fx = (double)px_map[(size_t)yi * W + xi];
+                fy = (double)py_map[(size_t)yi * W + xi];
+            } else {
+                const float2 f = composite_at2(src.comp, frame + src.frame_base, c_paf_x[k], yi, xi);
+                fx = (double)f.x;
+                fy = (double)f.y;
+            }
             dot = __dadd_rn(__dmul_rn(fx, ux), __dmul_rn(fy, uy));
         }
         const unsigned above = __ballot_sync(0xffffffffu, lane < kMid && dot > thre2);
@@ -89,21 +110,22 @@ __device__ __forceinline__ bool cand_before(double s1, long long o1, double s2, 
     return s1 > s2 || (s1 == s2 && o1 < o2);
 }
 
-__global__ void __launch_bounds__(256) limb_match_kernel(const int* __restrict__ part_begin, LimbBuffers lb,
-                                                         int* __restrict__ order /*[19][pair_capacity]*/,
-                                                         unsigned char* __restrict__ used /*[19][2][max_part]*/,
-                                                         int max_part) {
+__global__ void __launch_bounds__(256) limb_match_kernel(const FramePost* __restrict__ frames) {
     __shared__ double s_score[256];
     __shared__ long long s_ord[256];
     const int k = blockIdx.x;
+    const FramePost& fr = frames[blockIdx.y];
+    const int* __restrict__ part_begin = fr.pb.part_begin;
+    const LimbBuffers& lb = fr.lb;
+    const int max_part = lb.max_part;
     const int pa = c_limb_a[k], pb = c_limb_b[k];
     const int a0 = part_begin[pa], nA = part_begin[pa + 1] - a0;
     const int b0 = part_begin[pb], nB = part_begin[pb + 1] - b0;
     const int n = min(lb.cand_count[k], lb.pair_capacity);
     const double* sc = lb.cand_score + (size_t)k * lb.pair_capacity;
     const int* ij = lb.cand_ij + (size_t)k * lb.pair_capacity * 2;
-    int* ord = order + (size_t)k * lb.pair_capacity;
-    unsigned char* usedA = used + (size_t)k * 2 * max_part;
+    int* ord = lb.order + (size_t)k * lb.pair_capacity;
+    unsigned char* usedA = lb.used + (size_t)k * 2 * max_part;
     unsigned char* usedB = usedA + max_part;
 
     if (threadIdx.x == 0) lb.conn_count[k] = (nA == 0 || nB == 0) ? -1 : 0;   // -1: limb in special_k
@@ -162,8 +184,13 @@ __global__ void __launch_bounds__(256) limb_match_kernel(const int* __restrict__
 }
 
 // ---- subset assembly: one warp, rows in dynamic shared memory -----------------------------------------
-__global__ void __launch_bounds__(32) assemble_kernel(const double* __restrict__ cand, LimbBuffers lb) {
-    extern __shared__ double rows[];                 // [subset_capacity][20]
+__global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restrict__ frames) {
+    extern __shared__ double rows_shared[];          // [min(subset_capacity, kSubsetRowsShared)][20]
+    const FramePost& fr = frames[blockIdx.x];
+    const double* __restrict__ cand = fr.pb.candidates;
+    const LimbBuffers& lb = fr.lb;
+    // work rows: shared memory, or the frame's global work buffer once a frame has needed more rows than fit
+    double* rows = lb.rows_global ? lb.rows_global : rows_shared;
     const int lane = threadIdx.x;
     int nrows = 0;
     bool fail = false;
@@ -282,25 +309,46 @@ __global__ void __launch_bounds__(32) assemble_kernel(const double* __restrict__
     }
 }
 
+// counts + the first rows of the ordered candidates and of the pruned subsets -> the frame's result block, which one
+// device-to-host copy per batch then moves into pinned memory
+__global__ void __launch_bounds__(256) pack_results_kernel(const FramePost* __restrict__ frames) {
+    const FramePost& fr = frames[blockIdx.x];
+    FrameResults* out = fr.result;
+    if (out == nullptr) return;
+    const int tid = threadIdx.x;
+    if (tid == 0) out->counts[0] = *fr.pb.count;
+    if (tid < 19) out->counts[1 + tid] = fr.pb.part_begin[tid];
+    if (tid == 32) out->counts[20] = *fr.lb.subset_count;
+    if (tid >= 64 && tid < 68) out->counts[21 + tid - 64] = fr.lb.status[tid - 64];
+    const int nc = min(min(fr.pb.part_begin[18], fr.pb.capacity), kEagerCand) * 4;
+    for (int i = tid; i < nc; i += blockDim.x) out->cand[i] = fr.pb.candidates[i];
+    const int ns = min(min(*fr.lb.subset_count, fr.lb.subset_capacity), kEagerSubset) * 20;
+    for (int i = tid; i < ns; i += blockDim.x) out->subset[i] = fr.lb.subset[i];
+}
+
 }  // namespace
 
-// scratch_order: int[19*pair_capacity]; scratch_used: uchar[19*2*max_part]
-void paf_group_launch2(const float* paf_planar, int H, int W, const double* candidates, const int* part_begin,
-                       LimbBuffers lb, double thre2, int* scratch_order, unsigned char* scratch_used, int max_part,
-                       cudaStream_t stream) {
-    OPB_REQUIRE(lb.subset_capacity * 20 * 8 <= 200 * 1024, "subset capacity limited by shared memory (<= 1280 rows)");   // + 10 KB static staging
-    OPB_CUDA(cudaMemsetAsync(lb.cand_count, 0, sizeof(int) * kLimbs, stream));
-    OPB_CUDA(cudaMemsetAsync(lb.status, 0, sizeof(int) * 4, stream));
-    dim3 grid(64, kLimbs);
-    paf_score_kernel<<<grid, 256, 0, stream>>>(paf_planar, H, W, candidates, part_begin, lb, thre2);
+// The per-frame counters (cand_count, status) must be zero on entry: the caller clears the plan's counter slab once
+// per batch.  subset_capacity: the largest FramePost::lb.subset_capacity of the batch.
+void paf_group_launch(const MapSource& paf, int n_frames, int H, int W, const FramePost* frames_dev, double thre2,
+                      int subset_capacity, cudaStream_t stream) {
+    dim3 grid(64, kLimbs, n_frames);
+    if (paf.planar != nullptr) paf_score_kernel<true><<<grid, 256, 0, stream>>>(paf, H, W, frames_dev, thre2);
+    else paf_score_kernel<false><<<grid, 256, 0, stream>>>(paf, H, W, frames_dev, thre2);
     OPB_CUDA(cudaGetLastError());
-    limb_match_kernel<<<kLimbs, 256, 0, stream>>>(part_begin, lb, scratch_order, scratch_used, max_part);
+    limb_match_kernel<<<dim3(kLimbs, n_frames), 256, 0, stream>>>(frames_dev);
     OPB_CUDA(cudaGetLastError());
     static bool attr[64] = {};
     if (first_use_on_device(attr)) {
-        OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubsetRowsShared * 20 * 8));
     }
-    assemble_kernel<<<1, 32, (size_t)lb.subset_capacity * 20 * 8, stream>>>(candidates, lb);
+    const size_t rows_smem = (size_t)std::min(subset_capacity, kSubsetRowsShared) * 20 * 8;
+    assemble_kernel<<<n_frames, 32, rows_smem, stream>>>(frames_dev);
+    OPB_CUDA(cudaGetLastError());
+}
+
+void pack_results_launch(const FramePost* frames_dev, int n_frames, cudaStream_t stream) {
+    pack_results_kernel<<<n_frames, 256, 0, stream>>>(frames_dev);
     OPB_CUDA(cudaGetLastError());
 }
 

@@ -115,13 +115,13 @@ __global__ void upsample_x_kernel(const float* __restrict__ src, int ho, int wo,
 struct UpYParams {
     const float* tmp[kMaxScales];     // (C, ho, W) per scale
     const int* yfirst[kMaxScales];
-    const float* yw[kMaxScales];
+    const float* yw[kMaxScales];      // 1/n_scales folded in
     int ho[kMaxScales];
     int n_scales;
-    float inv_n;
 };
 
-// pass 2: out[c][y][x] = (1/n) * sum_s sum_k yw_s[y][k] * tmp_s[c][yfirst_s[y]+k][x]
+// pass 2 (generic shapes): out[c][y][x] = chain over scales s, taps k of fmaf(yw_s[y][k], tmp_s[c][yfirst_s[y]+k][x], .)
+// -- the same chain as the register-blocked kernel below and as composite.cuh (zero-weight strip rows are no-ops)
 template <int VEC>
 __global__ void upsample_y_kernel(const __grid_constant__ UpYParams p, int C, int H, int W, float* __restrict__ out) {
     const int xv = blockIdx.x * blockDim.x + threadIdx.x;
@@ -136,25 +136,20 @@ __global__ void upsample_y_kernel(const __grid_constant__ UpYParams p, int C, in
         const int f = p.yfirst[s][y];
         const int ho = p.ho[s];
         const float* t = p.tmp[s] + (size_t)c * ho * W + x;
-        float part[VEC];
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) part[v] = 0.f;
 #pragma unroll
         for (int k = 0; k < kUpTaps; ++k) {
             const float wgt = p.yw[s][y * kUpTaps + k];
             const int r = min(f + k, ho - 1);
             if (VEC == 4) {
                 const float4 q = *(const float4*)(t + (size_t)r * W);
-                part[0] = fmaf(wgt, q.x, part[0]);
-                part[1 % VEC] = fmaf(wgt, q.y, part[1 % VEC]);
-                part[2 % VEC] = fmaf(wgt, q.z, part[2 % VEC]);
-                part[3 % VEC] = fmaf(wgt, q.w, part[3 % VEC]);
+                acc[0] = fmaf(wgt, q.x, acc[0]);
+                acc[1 % VEC] = fmaf(wgt, q.y, acc[1 % VEC]);
+                acc[2 % VEC] = fmaf(wgt, q.z, acc[2 % VEC]);
+                acc[3 % VEC] = fmaf(wgt, q.w, acc[3 % VEC]);
             } else {
-                part[0] = fmaf(wgt, t[(size_t)r * W], part[0]);
+                acc[0] = fmaf(wgt, t[(size_t)r * W], acc[0]);
             }
         }
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) acc[v] += part[v] * p.inv_n;     // heatmap/len(multiplier), then +=
     }
     float* o = out + ((size_t)c * H + y) * W + x;
     if (VEC == 4)
@@ -258,7 +253,6 @@ void upsample_avg_launch2(const UpsampleScale* scales, int n_scales, int n_img, 
     UpYParams p;
     memset(&p, 0, sizeof(p));
     p.n_scales = n_scales;
-    p.inv_n = 1.0f / (float)n_scales;
     size_t off = 0;
     for (int s = 0; s < n_scales; ++s) {
         const UpsampleScale& u = scales[s];
@@ -356,39 +350,6 @@ __global__ void __launch_bounds__(128) preprocess_f32_kernel(const TIn* __restri
     o[2] = __float2bfloat16_rn(r[2]);
 }
 
-__device__ __forceinline__ int reflect101(int i, int n) {          // torch 'reflect': no edge repeat
-    if (n == 1) return 0;
-    if (i < 0) i = -i;
-    if (i >= n) i = 2 * n - 2 - i;
-    return min(max(i, 0), n - 1);
-}
-
-// utilmx.GaussianBlurConv (utilmx.py:243-263): depthwise 5x5 on a reflect-padded map.  Fixed operation order (taps in
-// row-major order; this file is compiled with --fmad=false so product and sum round separately) == the oracle's
-// blur5_fixed_order bit for bit; torch adds the same 25 products in an unspecified order.
-struct Blur5 { float w[25]; };
-constexpr int BW = 32, BH = 8;
-__global__ void __launch_bounds__(BW * BH) blur5_kernel(const float* __restrict__ in, float* __restrict__ out, int H, int W,
-                                                        const Blur5 k) {
-    __shared__ float tile[BH + 4][BW + 4];
-    const size_t plane = (size_t)blockIdx.z * H * W;
-    const int x0 = blockIdx.x * BW, y0 = blockIdx.y * BH;
-    const int tid = threadIdx.y * BW + threadIdx.x;
-    for (int i = tid; i < (BH + 4) * (BW + 4); i += BW * BH) {
-        const int ry = i / (BW + 4), rx = i - ry * (BW + 4);
-        tile[ry][rx] = __ldg(in + plane + (size_t)reflect101(y0 - 2 + ry, H) * W + reflect101(x0 - 2 + rx, W));
-    }
-    __syncthreads();
-    const int x = x0 + threadIdx.x, y = y0 + threadIdx.y;
-    if (x >= W || y >= H) return;
-    float acc = 0.f;
-#pragma unroll
-    for (int dy = 0; dy < 5; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 5; ++dx) acc = acc + k.w[dy * 5 + dx] * tile[threadIdx.y + dy][threadIdx.x + dx];
-    out[plane + (size_t)y * W + x] = acc;
-}
-
 }  // namespace
 
 void preprocess_f32_launch(const void* frames, bool frames_u8_hwc, int n, int H, int W, void* out_bf16, int h, int w,
@@ -401,20 +362,6 @@ void preprocess_f32_launch(const void* frames, bool frames_u8_hwc, int n, int H,
     else
         preprocess_f32_kernel<float><<<grid, 128, 0, stream>>>((const float*)frames, H, W, (__nv_bfloat16*)out_bf16, h, w, hp,
                                                                wp, x_first, x_w, y_first, y_w);
-    OPB_CUDA(cudaGetLastError());
-}
-
-void blur5_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream) {
-    static const float kw[5][5] = {{0.00078633f, 0.00655965f, 0.01330373f, 0.00655965f, 0.00078633f},      // utilmx.py:248-252
-                                   {0.00655965f, 0.05472157f, 0.11098164f, 0.05472157f, 0.00655965f},
-                                   {0.01330373f, 0.11098164f, 0.22508352f, 0.11098164f, 0.01330373f},
-                                   {0.00655965f, 0.05472157f, 0.11098164f, 0.05472157f, 0.00655965f},
-                                   {0.00078633f, 0.00655965f, 0.01330373f, 0.00655965f, 0.00078633f}};
-    Blur5 k;
-    memcpy(k.w, kw, sizeof(k.w));
-    OPB_REQUIRE(n_maps <= 65535, "blur5: too many maps in one launch");
-    dim3 grid(cdiv(W, BW), cdiv(H, BH), n_maps), block(BW, BH);
-    blur5_kernel<<<grid, block, 0, stream>>>(maps_planar, out_planar, H, W, k);
     OPB_CUDA(cudaGetLastError());
 }
 

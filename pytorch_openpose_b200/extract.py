@@ -433,6 +433,7 @@ class ExtractLedger(object):
         read back, exactly like the reference's readlines()."""
         if init:
             names = [f for f in os.listdir(self.datadir) if os.path.splitext(f)[1] in (".npy", ".pkl")]
+            self._drop_stale_claims(names)
             with open(self.path, "w") as f:
                 for name in names:
                     f.write("%s\n" % name)
@@ -443,6 +444,52 @@ class ExtractLedger(object):
     def add(self, name):
         with open(self.path, "a") as f:
             f.write("%s\n" % name)
+
+    # ---- claim files: `.video-XXX.claim` holding "host pid" of the worker that took the video ----
+    def claim_path(self, outname):
+        return os.path.join(self.datadir, "." + outname[:9] + ".claim")
+
+    def try_claim(self, outname):
+        """Atomically take a video: only one worker creates the claim file."""
+        import socket
+        try:
+            fd = os.open(self.claim_path(outname), os.O_CREAT | os.O_EXCL | os.O_WRONLY)
+        except FileExistsError:
+            return False
+        with os.fdopen(fd, "w") as f:
+            f.write("%s %d\n" % (socket.gethostname(), os.getpid()))
+        return True
+
+    def release(self, outname):
+        try:
+            os.remove(self.claim_path(outname))
+        except FileNotFoundError:
+            pass
+
+    def _drop_stale_claims(self, present):
+        """A rebuild of the ledger (init=True) re-opens every video without an output file, like the reference's
+        (srcmx/utilmx.py:190-208): claims left behind by a worker that died are removed.  A claim whose owner is a live
+        process on this host is kept (that worker is still busy with the video)."""
+        import socket
+        have = set(n[:9] for n in present)
+        for f in os.listdir(self.datadir):
+            if not (f.startswith(".") and f.endswith(".claim")):
+                continue
+            if f[1:10] in have:
+                continue
+            path = os.path.join(self.datadir, f)
+            try:
+                with open(path) as fh:
+                    host, pid = fh.read().split()
+                if host == socket.gethostname() and int(pid) != os.getpid():
+                    os.kill(int(pid), 0)                 # raises if the owner is gone
+                    continue
+            except (OSError, ValueError):
+                pass
+            try:
+                os.remove(path)
+            except FileNotFoundError:
+                pass
 
     def claimed(self, outname):
         """The reference's test: the first 9 characters ('video-XXX') of any ledger line (Batch_motion_Estimation.py:156)."""
@@ -482,8 +529,8 @@ def run_body_job(videofolder, datadir, recpoint, process_video, mode="body", ini
     characters of the file name), exactly the loop of `Test(code=0)`: the output name is appended to the ledger BEFORE
     the video is processed, and a name whose first nine characters are already in the ledger is skipped.  Several
     workers (one process per GPU) may share `datadir`; the reference relies on shuffling to keep them apart, here a
-    claim is additionally made atomic with an exclusive lock file next to the ledger, so two workers never take the
-    same video.  `process_video(videopath, outpath)` does the work (e.g. a lambda around `batch_body_extraction`).
+    claim is additionally made atomic with an exclusive claim file next to the ledger (removed when the video is done
+    or has failed; stale ones are cleared by init=True), so two workers never take the same video.  `process_video(videopath, outpath)` does the work (e.g. a lambda around `batch_body_extraction`).
     Returns the output names this worker produced."""
     led = ExtractLedger(datadir)
     if init or not os.path.exists(led.path):
@@ -498,12 +545,16 @@ def run_body_job(videofolder, datadir, recpoint, process_video, mode="body", ini
         outname = "video-%s-%s.pkl" % (filename[:3], mode)
         if led.claimed(outname):
             continue
-        try:                                            # atomic claim: only one worker creates the lock file
-            os.close(os.open(os.path.join(datadir, "." + outname[:9] + ".claim"), os.O_CREAT | os.O_EXCL | os.O_WRONLY))
-        except FileExistsError:
+        if not led.try_claim(outname):
             continue
         log(outname)
         led.add(outname)
-        process_video(os.path.join(videofolder, filename), os.path.join(datadir, outname))
+        try:
+            process_video(os.path.join(videofolder, filename), os.path.join(datadir, outname))
+        finally:
+            # finished: the ledger line (and the output file) keep the video closed.  Failed: the line stays, as in the
+            # reference, until a run with init=True rebuilds the ledger from the files present -- and the claim must
+            # not outlive this worker, or that run would skip the video forever.
+            led.release(outname)
         done.append(outname)
     return done

@@ -254,3 +254,53 @@ def test_two_workers_share_a_data_directory(video, tmp_path):
     for name in produced:
         assert np.array_equal(joblib.load(str(data / name)), ref)
     assert E.run_body_job(str(vids), str(data), REC, lambda a, b: 1 / 0, log=lambda m: None) == []   # nothing left
+
+
+def test_job_resumes_after_a_worker_died_inside_a_video(tmp_path):
+    """A worker that fails after claiming a video must not lock it forever (the reference rebuilds its ledger from the
+    files present, srcmx/utilmx.py:190-208, so an unfinished video is redone): the claim goes away with the failure,
+    claims left by a dead process are cleared by init=True, and the rerun processes exactly the unfinished videos."""
+    import subprocess
+    import sys
+    vids, data = tmp_path / "videos", tmp_path / "data"
+    vids.mkdir()
+    data.mkdir()
+    for k in range(3):
+        (vids / ("%03d-clip.avi" % k)).write_bytes(b"x")
+    calls = []
+
+    def process(videopath, outpath):
+        calls.append(os.path.basename(videopath))
+        if "001" in videopath:
+            raise RuntimeError("decoder died")
+        with open(outpath, "wb") as f:
+            f.write(b"track")
+
+    with pytest.raises(RuntimeError):
+        E.run_body_job(str(vids), str(data), REC, process, init=True, log=lambda m: None)
+    assert calls == ["000-clip.avi", "001-clip.avi"]
+    assert not [f for f in os.listdir(str(data)) if f.endswith(".claim")]          # nothing left locked
+    # a worker killed outright (no finally) leaves its claim file: simulate with a claim owned by a dead pid
+    dead = subprocess.Popen([sys.executable, "-c", "pass"])
+    dead.wait()
+    import socket
+    (data / ".video-002.claim").write_text("%s %d\n" % (socket.gethostname(), dead.pid))
+    # without init the ledger still lists video-001 (appended before processing, like the reference) -> skipped
+    calls.clear()
+    assert E.run_body_job(str(vids), str(data), REC, process, log=lambda m: None) == []
+    # init=True: ledger rebuilt from the files present, stale claims dropped -> 001 fails again, then 002 is done
+    calls.clear()
+    ok = lambda videopath, outpath: (calls.append(os.path.basename(videopath)), open(outpath, "wb").write(b"track"))
+    assert E.run_body_job(str(vids), str(data), REC, ok, init=True, log=lambda m: None) == ["video-001-body.pkl",
+                                                                                           "video-002-body.pkl"]
+    assert calls == ["001-clip.avi", "002-clip.avi"]
+    assert not [f for f in os.listdir(str(data)) if f.endswith(".claim")]
+    # a claim held by a LIVE worker on this host survives a rebuild by somebody else
+    (vids / "003-clip.avi").write_bytes(b"x")
+    live = subprocess.Popen([sys.executable, "-c", "import time; time.sleep(30)"])
+    try:
+        (data / ".video-003.claim").write_text("%s %d\n" % (socket.gethostname(), live.pid))
+        assert E.run_body_job(str(vids), str(data), REC, ok, init=True, log=lambda m: None) == []
+    finally:
+        live.kill()
+        live.wait()
