@@ -11,18 +11,30 @@ namespace opb {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string& m) { g_last_error = m; }
 
+// OPB_DEBUG_ERRORS=1: report CUDA errors that are pending when an entry point is entered or left (an unchecked failing
+// call of this library or of another CUDA user in the process would otherwise surface at some later launch check)
+static void report_pending(const char* fn, const char* when) {
+    static const bool on = getenv("OPB_DEBUG_ERRORS") != nullptr;
+    if (!on) return;
+    const cudaError_t e = cudaPeekAtLastError();
+    if (e != cudaSuccess) fprintf(stderr, "[opb] pending CUDA error %s %s: %s\n", when, fn, cudaGetErrorString(e));
+}
+
 template <typename F>
-static int guarded(F&& f) {
+static int guarded(F&& f, const char* fn = __builtin_FUNCTION()) {
+    report_pending(fn, "on entry to");
+    int rc = OPB_OK;
     try {
         f();
-        return OPB_OK;
     } catch (const Error& e) {
         set_last_error(e.what());
-        return e.code;
+        rc = e.code;
     } catch (const std::exception& e) {
         set_last_error(e.what());
-        return OPB_ERR_INVALID;
+        rc = OPB_ERR_INVALID;
     }
+    report_pending(fn, "on return from");
+    return rc;
 }
 
 struct ScaleDims {

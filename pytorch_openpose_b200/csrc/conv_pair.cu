@@ -36,6 +36,8 @@ struct QProb {
     int out_cstride, cout_store;
     int n_tiles_n, cin_chunks;
     int pair_begin, flags;
+    int n_full_img;              // super-tiles per image whose two halves both hold pixels (they come first in the tile order)
+    int noskip;                  // A/B switch: multiply empty halves too
     int vsplit;                  // 0: the two 128-pixel halves of a super-tile sit side by side (8 cols x 16 rows each),
                                  // 1: stacked (16 cols x 8 rows each) -- chosen per problem for the least padding
 };
@@ -89,23 +91,40 @@ __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, in
     TileCoord c;
     c.real = mt < q.m_tiles;
     if (!c.real) mt = q.m_tiles - 1;
+    // Tile order of a problem: first every super-tile with two occupied halves (all images), then the edge tiles whose
+    // second half lies outside the image (last tile row when the halves are stacked, last tile column when they sit
+    // side by side) -- so the two tiles of a pair agree on which halves to skip, except for at most one pair.
     const int per_img = q.tiles_x * q.tiles_y;
-    const int img = mt / per_img;
-    const int r = mt - img * per_img;
-    int txi, tyi;
-    if (q.vsplit) {              // row-major: the two tiles of a pair are horizontal neighbours (same rows -> same empty half)
-        tyi = r / q.tiles_x;
-        txi = r - tyi * q.tiles_x;
-    } else {                     // column-major: vertical neighbours (same columns)
-        txi = r / q.tiles_y;
-        tyi = r - txi * q.tiles_y;
+    const int n_edge_img = per_img - q.n_full_img;
+    int img, txi, tyi;
+    if (mt < q.N * q.n_full_img) {
+        img = mt / q.n_full_img;
+        const int r = mt - img * q.n_full_img;
+        if (q.vsplit) {
+            tyi = r / q.tiles_x;
+            txi = r - tyi * q.tiles_x;
+        } else {
+            txi = r / q.tiles_y;
+            tyi = r - txi * q.tiles_y;
+        }
+    } else {
+        const int e = mt - q.N * q.n_full_img;
+        img = e / n_edge_img;
+        const int i = e - img * n_edge_img;
+        if (q.vsplit) {
+            txi = i;
+            tyi = q.tiles_y - 1;
+        } else {
+            txi = q.tiles_x - 1;
+            tyi = i;
+        }
     }
     c.pi = pi;
     c.img = img;
     c.x0 = txi * kTile;
     c.y0 = tyi * kTile;
     c.n0 = nt * block_n;
-    const bool second = q.vsplit ? (c.y0 + 8 < q.H) : (c.x0 + 8 < q.W);
+    const bool second = q.noskip || (q.vsplit ? (c.y0 + 8 < q.H) : (c.x0 + 8 < q.W));
     c.halves = c.real ? (second ? 3 : 1) : 0;
     return c;
 }
@@ -420,7 +439,11 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
             // columns to 16 and rows to 8 (e.g. 41x23: 48x32 vs 48x24; 82x46: 88x48 vs 96x48)
             static const char* force = getenv("OPB_PAIR_SPLIT");
             const long side = (long)cdiv(W, 8) * 8 * cdiv(H, 16) * 16, stacked = (long)cdiv(W, 16) * 16 * cdiv(H, 8) * 8;
+            static const char* noskip = getenv("OPB_PAIR_NOSKIP");
             q.vsplit = force ? atoi(force) : (stacked < side ? 1 : 0);
+            q.noskip = noskip ? 1 : 0;
+            const bool edge = !q.noskip && (q.vsplit ? ((q.tiles_y - 1) * kTile + 8 >= H) : ((q.tiles_x - 1) * kTile + 8 >= W));
+            q.n_full_img = q.tiles_x * q.tiles_y - (edge ? (q.vsplit ? q.tiles_x : q.tiles_y) : 0);
         }
         pairs += q.m_pairs * q.n_tiles_n;
 

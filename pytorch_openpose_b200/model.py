@@ -81,3 +81,12 @@ class handpose_model(nn.Module):
         for s in range(2, 7):
             out = getattr(self, "model%d" % s)(torch.cat([out, feat], 1))
         return out
+
+
+def random_checkpoint(kind, seed=0):
+    """A random-init checkpoint in the reference's file format (caffe-keyed flat dict, src/util.py:36-40), i.e. what
+    `torch.manual_seed(seed); bodypose_model()` holds -- for benchmarks and smoke runs: no trained weights exist
+    offline."""
+    torch.manual_seed(seed)
+    net = bodypose_model() if kind == "body" else handpose_model()
+    return {k.split(".", 1)[1]: v.detach().clone() for k, v in net.state_dict().items()}
