@@ -135,10 +135,134 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+
+# ---- further BASELINE.json configurations, measured through the public API at every N (all ranks run, max over ranks) ----
+def extra_hand_c3(local, barrier, max_over_ranks, world):
+    """config 3: Hand() on 256 synthetic 368x368 crops (host memory in, key points out), 4 scales like src/hand.py:26
+    and one scale."""
+    import torch
+    from pytorch_openpose_b200 import Hand
+    from pytorch_openpose_b200.model import random_checkpoint
+    crops = np.random.default_rng(7).integers(0, 256, (256, 368, 368, 3), dtype=np.uint8)
+    sd = random_checkpoint("hand", 0)
+    out = {"workload": "Hand()(crops): 256 synthetic 368x368 crops from host memory, wall clock incl. H2D / D2H"}
+    for tag, scales, gflop in (("4scale", [0.5, 1.0, 1.5, 2.0], 1547.82), ("1scale", [1.0], 206.38)):
+        hand = Hand(sd, scale_search=scales, device=local)
+        hand(crops)                                     # builds the plans
+        reps = 2 if tag == "4scale" else 4
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            hand(crops)
+        torch.cuda.synchronize()
+        dt = max_over_ranks((time.perf_counter() - t0) / reps)
+        out[tag] = {"crops_per_s": round(256 * world / dt, 1), "ms_per_256": round(dt * 1e3, 2),
+                    "conv_tflops_per_gpu": round(gflop * 256 / dt * 1e-3, 1)}
+        del hand
+    peak, _, _ = measured_peaks()
+    out["roofline"] = {"bound": "tensor", "achieved": out["4scale"]["conv_tflops_per_gpu"], "peak": peak, "unit": "TFLOP/s",
+                       "frac": round(out["4scale"]["conv_tflops_per_gpu"] / peak, 3),
+                       "note": "whole call incl. copies and post-processing over the algorithmic conv FLOPs (1547.8 GFLOP/crop)"}
+    return out
+
+
+def extra_bodyhand_c4(local, rank, barrier, max_over_ranks, world, streams=2, B=8, F=32, steps=4):
+    """config 4: 720p stream, body (4 scales) + two hand crops (4 scales) per frame.  Random-init weights find no
+    person, so the two hand boxes are fixed 184x184 crops; left hand mirrored like the caller does."""
+    import torch
+    from pytorch_openpose_b200 import Body, Hand
+    from pytorch_openpose_b200.model import random_checkpoint
+    body = Body(random_checkpoint("body", 0), scale_search=SCALES, device=local)
+    hand = Hand(random_checkpoint("hand", 0), device=local)
+    bs = [body.net.session() for _ in range(streams)]
+    hs = [hand.net.session() for _ in range(streams)]
+    pool = torch.from_numpy(synth_frames(32, 77 + rank)).pin_memory()
+    frames = pool.numpy()
+    boxes = [(700, 300, 184), (400, 300, 184)]
+
+    def step(i):
+        inflight = [False] * streams
+        for b in range(F // B):
+            si = b % streams
+            if inflight[si]:
+                body.collect_batch(bs[si])
+                hand.collect(hs[si])
+            idx = (i * F + b * B) % 32
+            fr = frames[idx:idx + B]
+            body.submit_batch(fr, bs[si], where=2)
+            crops = np.stack([fr[f, y:y + w, x:x + w] if k == 0 else fr[f, y:y + w, x:x + w][:, ::-1]
+                              for f in range(B) for k, (x, y, w) in enumerate(boxes)])
+            hand.submit(crops, hs[si])
+            inflight[si] = True
+        for si in range(streams):
+            if inflight[si]:
+                body.collect_batch(bs[si])
+                hand.collect(hs[si])
+
+    for i in range(2):
+        step(i)
+    barrier()
+    bs[0].mark(0)
+    for i in range(steps):
+        step(2 + i)
+    for s in bs + hs:
+        s.mark(1)
+    torch.cuda.synchronize()
+    ms = max_over_ranks(max(bs[0].elapsed_ms(0, s, 1) for s in bs + hs))
+    n = F * steps * world
+    peak, _, _ = measured_peaks()
+    tf = 6730.4 * F * steps / ms
+    return {"value": round(n / (ms * 1e-3), 1), "unit": "frames/s", "ms_per_frame_per_gpu": round(ms / (F * steps), 3),
+            "conv_tflops_per_gpu": round(tf, 1),
+            "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(tf / peak, 3)},
+            "workload": "body 4-scale + two 184x184 hand crops 4-scale per 720p frame, pinned host frames, host crops "
+                        "(CUDA events over %d frames per GPU)" % (F * steps)}
+
+
+def extra_e2e_decode(local, rank, barrier, max_over_ranks, world, n_frames=256):
+    """Decode-inclusive leg: MJPG 720p file -> cv2.VideoCapture threads -> pinned batch ring -> Body 4-scale -> pose
+    track (pytorch_openpose_b200.extract, the reference's Extract_MotionData_from_Video).  Every rank decodes its own
+    file at the same time with cpu_count / world decoder threads (at most 4), so the figure shows whether host decode
+    bends the 1 -> 8 curve.  Wall clock, max over ranks."""
+    import tempfile
+    import cv2
+    import torch
+    from pytorch_openpose_b200 import Body, extract
+    from pytorch_openpose_b200.model import random_checkpoint
+    d = tempfile.mkdtemp(prefix="opb_bench_%d_" % rank)
+    path = os.path.join(d, "v.avi")
+    wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"MJPG"), 25, (W, H))
+    base = synth_frames(8, 500 + rank)
+    for i in range(n_frames):
+        wr.write(np.roll(base[i % 8], 7 * i, axis=1))
+    wr.release()
+    workers = max(1, min(4, (os.cpu_count() or 1) // world))
+    body = Body(random_checkpoint("body", 0), scale_search=SCALES, device=local)
+    quiet = lambda m: None
+    extract.extract_motion_from_video(path, os.path.join(d, "w.pkl"), None, body, mode="body", batch=8, sessions=3,
+                                      log=quiet, decode_workers=workers)                  # plans + pinned rings
+    barrier()
+    t0 = time.perf_counter()
+    mat = extract.extract_motion_from_video(path, os.path.join(d, "o.pkl"), None, body, mode="body", batch=8, sessions=3,
+                                            log=quiet, decode_workers=workers)
+    torch.cuda.synchronize()
+    dt = max_over_ranks(time.perf_counter() - t0)
+    # decode alone, same threads, all ranks at once
+    barrier()
+    t0 = time.perf_counter()
+    n = sum(len(item[0]) for item in extract.FrameBatches(path, None, batch=8, depth=5, pinned=True, workers=workers))
+    ddt = max_over_ranks(time.perf_counter() - t0)
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    return {"value": round(len(mat) * world / dt, 1), "unit": "frames/s", "decode_only_frames_per_s": round(n * world / ddt, 1),
+            "decoder_threads_per_rank": workers, "host_cores": os.cpu_count(), "frames_per_rank": int(len(mat)),
+            "workload": "720p MJPG file per rank -> decode threads -> pinned ring -> Body 4-scale -> pose track file; wall clock"}
+
+
 def run_ours(args):
     import torch
-    from oracle import openpose_oracle as O            # weights generator only (random-init, seed 0)
     from pytorch_openpose_b200 import Body, _lib
+    from pytorch_openpose_b200.model import random_checkpoint      # random-init weights, seed 0 (no checkpoints offline)
     rank, local, world = rank_info()
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
@@ -167,7 +291,7 @@ def run_ours(args):
         return float(t.item())
 
     F, K, Wm = args.frames_per_step, args.steps, args.warmup
-    body = Body(O.make_weights("body", 0), scale_search=SCALES, device=local)
+    body = Body(random_checkpoint("body", 0), scale_search=SCALES, device=local)
     sessions = [body.net.session() for _ in range(args.streams)]
     frames_host = torch.from_numpy(synth_frames(POOL_FRAMES, 1000 + rank)).pin_memory()
     frames_dev = frames_host.cuda()
@@ -271,6 +395,7 @@ def run_ours(args):
     grouping = None
     if rank == 0:
         import ctypes
+        from oracle import openpose_oracle as O        # checker / CPU leg only: the synthetic 50-person scene and its CPU timing
         heat50, paf50, _ = O.synthetic_scene(H, W, (10, 5), seed=0)
         d_heat = torch.from_numpy(np.ascontiguousarray(heat50.transpose(2, 0, 1), dtype=np.float32)).cuda()
         d_paf = torch.from_numpy(np.ascontiguousarray(paf50.transpose(2, 0, 1), dtype=np.float32)).cuda()
@@ -292,6 +417,19 @@ def run_ours(args):
         cpu = {"value": 2.0 / float(np.sum(t)), "unit": "frames/s", "cores": threads, "kind": "port",
                "sample": "2 full 720p 4-scale frames through the oracle restatement of src/body.py (no warm-up)"}
 
+    extras = {}
+    if not args.no_extras:
+        del sessions, frames_dev
+        torch.cuda.empty_cache()
+        for name, fn in (("hand_c3", lambda: extra_hand_c3(local, barrier, max_over_ranks, world)),
+                         ("bodyhand_c4", lambda: extra_bodyhand_c4(local, rank, barrier, max_over_ranks, world)),
+                         ("e2e_decode", lambda: extra_e2e_decode(local, rank, barrier, max_over_ranks, world))):
+            try:
+                extras[name] = fn()
+            except Exception as e:                      # an extra leg must never cost the headline line
+                extras[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            barrier()
+
     if rank == 0:
         total_frames = F * K * world
         d2h = F * (4 * 25 + 2048 * 32 + 128 * 160)          # per frame: counts + eager candidate / subset rows
@@ -305,7 +443,7 @@ def run_ours(args):
                 "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W * 3,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / K},
                 "gpu_launches": launches, "clocks": clocks, "roofline": roof, "cpu_baseline": cpu,
-                "paf_grouping": grouping,
+                "paf_grouping": grouping, "extra": extras,
                 "stage_ms_per_frame": {k: round(v, 4) for k, v in stages.items()}}
         # HBM-bound stages: algorithmic bytes per frame / measured stage time vs the measured copy bandwidth
         px_in = sum(hp * wp for hp, wp in ((184, 328), (368, 656), (552, 984), (736, 1312)))
@@ -343,6 +481,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="frames per batched submit (one launch per CNN layer per batch)")
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the config-3 / config-4 / decode-inclusive legs")
     ap.add_argument("--layers", default=None, help="write the per-launch profile of one frame to this CSV")
     args = ap.parse_args()
     if args.impl == "reference":

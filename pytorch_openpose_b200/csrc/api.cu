@@ -5,6 +5,7 @@
 #include <cstring>
 #include <algorithm>
 #include <cmath>
+#include <mutex>
 
 namespace opb {
 
@@ -964,8 +965,17 @@ int opb_net_load_layer(opb_net* net, const char* name, const float* weight, cons
 int opb_net_finalize(opb_net* net) {
     return guarded([&] { finalize_net(net); });
 }
+static std::mutex g_lifetime;      // net <-> session reference counts
 int opb_net_destroy(opb_net* net) {
-    return guarded([&] { delete net; });
+    return guarded([&] {
+        if (!net) return;
+        std::lock_guard<std::mutex> lock(g_lifetime);
+        if (net->sessions > 0) {
+            net->released = true;          // freed by its last session
+            return;
+        }
+        delete net;
+    });
 }
 int opb_net_layer_count(int kind) {
     if (kind != OPB_NET_BODY && kind != OPB_NET_HAND) return OPB_ERR_INVALID;
@@ -992,16 +1002,22 @@ int opb_session_create(opb_net* net, opb_session** out) {
         s->net = net;
         OPB_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
         OPB_CUDA(cudaEventCreateWithFlags(&s->done, cudaEventDisableTiming));
+        {
+            std::lock_guard<std::mutex> lock(g_lifetime);
+            ++net->sessions;
+        }
         *out = s;
     });
 }
 int opb_session_destroy(opb_session* s) {
     return guarded([&] {
-        if (s) {
-            cudaSetDevice(s->net->ctx->device);
-            cudaStreamSynchronize(s->stream);
-        }
+        if (!s) return;
+        opb_net* net = s->net;
+        OPB_CUDA(cudaSetDevice(net->ctx->device));
+        cudaStreamSynchronize(s->stream);
         delete s;
+        std::lock_guard<std::mutex> lock(g_lifetime);
+        if (--net->sessions == 0 && net->released) delete net;
     });
 }
 

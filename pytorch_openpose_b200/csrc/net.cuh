@@ -48,6 +48,10 @@ struct opb_net {
     std::map<std::string, opb::DevLayer> dev;
     bool finalized = false;
     std::vector<void*> owned;
+    // sessions keep their network alive: opb_net_destroy on a net that still has sessions only marks it, the last
+    // opb_session_destroy frees it (a garbage collector may finalise the two host objects in either order)
+    int sessions = 0;
+    bool released = false;
     ~opb_net();
 };
 

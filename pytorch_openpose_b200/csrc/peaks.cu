@@ -295,19 +295,38 @@ __device__ __forceinline__ void tile_part(const PeakParams& p, const TileSmem& s
             const CompositeScale& c = cm.sc[s];
             const int nr = sm.fp_nr[s], nc = sm.fp_nc[s], r0 = sm.fp_r0[s], c0 = sm.fp_c0[s];
             const float* los = lo + sm.fp_off[s];
-            // x pass: rows of the footprint x window columns
-            for (int i = tid; i < nr * G::RAW_W; i += kThreads) {
-                const int r = i / G::RAW_W, cx = i - r * G::RAW_W;
-                const int ix = x0 - G::HALO + cx;
-                float t = 0.f;
-                if (ix >= xlo && ix <= xhi) {
-                    const int fx = __ldg(c.xf + ix);
-                    const float* row = los + r * nc - c0;
+            // x pass: rows of the footprint x window columns.  A lane owns the columns lane, lane + 32, lane + 64 and keeps
+            // their tap tables in registers; the warps stride over the rows.
+            {
+                constexpr int CPL = (G::RAW_W + 31) / 32;
+                const int lane = tid & 31, warp = tid >> 5;
+                int fxr[CPL];
+                float wxr[CPL][kUpTaps];
 #pragma unroll
-                    for (int k = 0; k < kUpTaps; ++k)
-                        t = fmaf(__ldg(c.xw + (size_t)ix * kUpTaps + k), row[min(fx + k, c.wo - 1)], t);
+                for (int q = 0; q < CPL; ++q) {
+                    const int cx = lane + 32 * q;
+                    const int ix = x0 - G::HALO + cx;
+                    const bool ok = cx < G::RAW_W && ix >= xlo && ix <= xhi;
+                    fxr[q] = ok ? __ldg(c.xf + ix) - c0 : -1;
+#pragma unroll
+                    for (int k = 0; k < kUpTaps; ++k) wxr[q][k] = ok ? __ldg(c.xw + (size_t)ix * kUpTaps + k) : 0.f;
                 }
-                xs[i] = t;
+                const int last = c.wo - 1 - c0;
+                for (int r = warp; r < nr; r += kThreads / 32) {
+                    const float* row = los + r * nc;
+#pragma unroll
+                    for (int q = 0; q < CPL; ++q) {
+                        const int cx = lane + 32 * q;
+                        if (cx < G::RAW_W) {
+                            float t = 0.f;
+                            if (fxr[q] >= 0) {
+#pragma unroll
+                                for (int k = 0; k < kUpTaps; ++k) t = fmaf(wxr[q][k], row[min(fxr[q] + k, last)], t);
+                            }
+                            xs[r * G::RAW_W + cx] = t;
+                        }
+                    }
+                }
             }
             __syncthreads();
             // y pass: (strip, column) items, 8 output rows each
@@ -337,29 +356,29 @@ __device__ __forceinline__ void tile_part(const PeakParams& p, const TileSmem& s
             }
             __syncthreads();
         }
+        bool bad = false;
 #pragma unroll
         for (int j = 0; j < G::SLOTS; ++j) {
             const int item = tid + j * kThreads;
             const int b = item / G::RAW_W, cx = item - b * G::RAW_W;
             const int ix = x0 - G::HALO + cx;
             if (item < G::STRIPS * G::RAW_W) {
+                const int iy0 = y0 - G::ROW_OFF + b * 8;
+                const bool col_ok = ix >= xlo && ix <= xhi;
+                const int i_lo = col_ok ? ylo - iy0 : 8, i_hi = yhi - iy0;      // rows of the strip inside the window
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    const int ry = b * 8 + i;
-                    const int iy = y0 - G::ROW_OFF + ry;
                     const float v = acc[j][i];
-                    raw[ry * G::RAW_W + cx] = v;
-                    if (iy >= ylo && iy <= yhi && ix >= xlo && ix <= xhi) {
-                        if (v == v) {
-                            vmin = fminf(vmin, v);
-                            vmax = fmaxf(vmax, v);
-                        } else {
-                            vmax = INFINITY;
-                        }
+                    raw[(b * 8 + i) * G::RAW_W + cx] = v;
+                    if (i >= i_lo && i <= i_hi) {
+                        vmin = fminf(vmin, v);                       // fminf / fmaxf drop a NaN operand ...
+                        vmax = fmaxf(vmax, v);
+                        bad |= v != v;                               // ... so it is tracked separately: never skip on NaN
                     }
                 }
             }
         }
+        if (bad) vmax = INFINITY;
     }
     block_minmax(vmin, vmax, sm.red);                    // also the barrier that publishes raw / flags
 
