@@ -418,7 +418,9 @@ def run_ours(args):
                "sample": "2 full 720p 4-scale frames through the oracle restatement of src/body.py (no warm-up)"}
 
     extras = {}
+    n_streams = len(sessions)
     if not args.no_extras:
+        n_streams = len(sessions)
         del sessions, frames_dev
         torch.cuda.empty_cache()
         for name, fn in (("hand_c3", lambda: extra_hand_c3(local, barrier, max_over_ranks, world)),
@@ -437,7 +439,7 @@ def run_ours(args):
                 "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
                 "config": {"workload": "Body() 4-scale [0.5,1.0,1.5,2.0] on synthetic 1280x720 frames, random-init bodypose_model",
-                           "frames_per_step": F, "frames_per_batch": B, "streams": len(sessions),
+                           "frames_per_step": F, "frames_per_batch": B, "streams": n_streams,
                            "parallelism": "frame-sharded replicas x%d" % world,
                            "l2": "pool of %d distinct frames (221 MB) and ~1 GB of activations per frame exceed the 126 MB L2" % POOL_FRAMES},
                 "e2e": {"value": total_frames / (ms_e2e * 1e-3), "unit": "frames/s", "h2d_bytes_per_step": F * H * W * 3,

@@ -28,15 +28,26 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
     return i >= n ? period - 1 - i : i;
 }
 
+// Ragged batches (crops of different sizes in one launch, the per-frame caller's hand boxes): `dims` holds the side
+// length of every (square) crop, the planes of a crop are stored densely with that width at a fixed stride `ps`, and
+// the grids are sized for the largest crop; dims == null means one size (h, w) for all, ps = h * w.
+#define OPB_HAND_GEOM(crop)                  \
+    if (dims) {                              \
+        h = w = dims[crop];                  \
+    }
+
 __global__ void __launch_bounds__(256) hand_smooth_kernel(const float* __restrict__ heat, int h, int w, int chan_stride_maps,
                                                           const GaussTaps taps, double thre, int* __restrict__ labels,
-                                                          double* __restrict__ smoothed_out) {
+                                                          double* __restrict__ smoothed_out, const int* __restrict__ dims,
+                                                          size_t ps) {
     __shared__ double raw[RAW_H][RAW_W];
     __shared__ double ver[TH][RAW_W];
     const int m = blockIdx.z;                                   // map index = crop * 21 + part
     const int crop = m / 21, part = m - crop * 21;
-    const float* map = heat + ((size_t)crop * chan_stride_maps + part) * h * w;
+    OPB_HAND_GEOM(crop)
     const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH;
+    if (x0 >= w || y0 >= h) return;
+    const float* map = heat + ((size_t)crop * chan_stride_maps + part) * ps;
     const int tid = threadIdx.x;
     __shared__ int s_row[RAW_H], s_col[RAW_W];
     if (tid < RAW_H) s_row[tid] = reflect_idx(y0 - R + tid, h);
@@ -75,7 +86,7 @@ __global__ void __launch_bounds__(256) hand_smooth_kernel(const float* __restric
 #pragma unroll
         for (int d = R; d >= 1; --d)
             acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ver[ty][tx + R - d], ver[ty][tx + R + d]), taps.w[d]));
-        const size_t idx = (size_t)m * h * w + (size_t)y * w + x;
+        const size_t idx = (size_t)m * ps + (size_t)y * w + x;
         labels[idx] = acc > thre ? y * w + x : -1;
         if (smoothed_out) smoothed_out[idx] = acc;
     }
@@ -113,11 +124,12 @@ __device__ void uf_union(int* L, int a, int b) {
 // of the component), (3) run heads are compressed to their root, (4) every pixel resolves label[label[i]].
 
 // (1) one warp per image row
-__global__ void hand_runs_kernel(int* __restrict__ labels, int h, int w) {
+__global__ void hand_runs_kernel(int* __restrict__ labels, int h, int w, const int* __restrict__ dims, size_t ps) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
+    OPB_HAND_GEOM(blockIdx.y / 21)
     if (row >= h) return;
-    int* L = labels + ((size_t)blockIdx.y * h + row) * w;
+    int* L = labels + (size_t)blockIdx.y * ps + (size_t)row * w;
     int carry = -1;                                     // head of the run that reaches the start of this segment
     for (int x0 = 0; x0 < w; x0 += 32) {
         const int x = x0 + lane;
@@ -136,11 +148,12 @@ __global__ void hand_runs_kernel(int* __restrict__ labels, int h, int w) {
 }
 
 // (2) unite every run with the runs of the row above that touch it (columns xs-1 .. xe+1)
-__global__ void hand_merge_kernel(int* __restrict__ labels, int h, int w) {
+__global__ void hand_merge_kernel(int* __restrict__ labels, int h, int w, const int* __restrict__ dims, size_t ps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= w || y == 0) return;
-    int* L = labels + (size_t)blockIdx.z * h * w;
+    OPB_HAND_GEOM(blockIdx.z / 21)
+    if (x >= w || y == 0 || y >= h) return;
+    int* L = labels + (size_t)blockIdx.z * ps;
     const int i = y * w + x;
     const int mine = L[i];
     if (mine < 0) return;
@@ -157,11 +170,12 @@ __global__ void hand_merge_kernel(int* __restrict__ labels, int h, int w) {
 }
 
 // (3) compress run heads to their roots
-__global__ void hand_compress_kernel(int* __restrict__ labels, int h, int w) {
+__global__ void hand_compress_kernel(int* __restrict__ labels, int h, int w, const int* __restrict__ dims, size_t ps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
-    if (x >= w) return;
-    int* L = labels + (size_t)blockIdx.z * h * w;
+    OPB_HAND_GEOM(blockIdx.z / 21)
+    if (x >= w || y >= h) return;
+    int* L = labels + (size_t)blockIdx.z * ps;
     const int i = y * w + x;
     if (L[i] < 0) return;
     const bool head = x == 0 || L[i - 1] < 0;
@@ -172,21 +186,22 @@ __global__ void hand_compress_kernel(int* __restrict__ labels, int h, int w) {
 
 // (4) resolve every pixel and accumulate the raw-map sum of its component
 __global__ void hand_flatten_kernel(const float* __restrict__ heat, int chan_stride_maps, int* __restrict__ labels,
-                                    double* __restrict__ sums, int h, int w) {
+                                    double* __restrict__ sums, int h, int w, const int* __restrict__ dims, size_t ps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
     const int y = blockIdx.y;
     const int m = blockIdx.z;
     const int crop = m / 21, part = m - crop * 21;
-    int* L = labels + (size_t)m * h * w;
+    OPB_HAND_GEOM(crop)
+    int* L = labels + (size_t)m * ps;
     const int i = y * w + x;
     int root = -1;
     double v = 0.0;
-    if (x < w && L[i] >= 0) {
+    if (x < w && y < h && L[i] >= 0) {
         root = __ldcg(L + __ldcg(L + i));              // pixel -> run head -> root
         // a run head may itself still point one hop short if it was hooked after its own compression pass started
         root = uf_find(L, root);
         L[i] = root;
-        v = (double)heat[((size_t)crop * chan_stride_maps + part) * h * w + i];
+        v = (double)heat[((size_t)crop * chan_stride_maps + part) * ps + i];
     }
     // warp-aggregated atomics: lanes of a warp almost always share one root
     const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
@@ -196,9 +211,9 @@ __global__ void hand_flatten_kernel(const float* __restrict__ heat, int chan_str
         double tot = v;
 #pragma unroll
         for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sums[(size_t)m * h * w + root], tot);
+        if ((threadIdx.x & 31) == 0) atomicAdd(&sums[(size_t)m * ps + root], tot);
     } else {
-        atomicAdd(&sums[(size_t)m * h * w + root], v);
+        atomicAdd(&sums[(size_t)m * ps + root], v);
     }
 }
 
@@ -230,14 +245,16 @@ __device__ Best block_best(Best mine, Best* s) {
 __global__ void __launch_bounds__(1024) hand_select_kernel(const float* __restrict__ heat, int chan_stride_maps,
                                                            const int* __restrict__ labels,
                                                            const double* __restrict__ sums, int h, int w,
-                                                           double* __restrict__ peaks) {
+                                                           double* __restrict__ peaks, const int* __restrict__ dims,
+                                                           size_t ps) {
     __shared__ Best s[32];
     const int m = blockIdx.x;
     const int crop = m / 21, part = m - crop * 21;
+    OPB_HAND_GEOM(crop)
     const int n = h * w;
-    const int* L = labels + (size_t)m * n;
-    const double* S = sums + (size_t)m * n;
-    const float* map = heat + ((size_t)crop * chan_stride_maps + part) * n;
+    const int* L = labels + (size_t)m * ps;
+    const double* S = sums + (size_t)m * ps;
+    const float* map = heat + ((size_t)crop * chan_stride_maps + part) * ps;
     Best mine{0.0, -1};
     for (int i = threadIdx.x; i < n; i += blockDim.x)
         if (L[i] == i) mine = better(mine, Best{S[i], i});      // roots only
@@ -273,7 +290,7 @@ __global__ void hand_mask_kernel(const float* __restrict__ heat, int h, int w, i
 }  // namespace
 
 static void hand_components_launch(const float* heat_planar, int maps, int chan_stride_maps, int h, int w, HandBuffers hb,
-                                   cudaStream_t stream);
+                                   const int* dims, size_t ps, cudaStream_t stream);
 
 // Batch_hand post-processing (srcmx/Batch_model.py:387-406): threshold, component sums and the maximum all on the
 // blurred map that is passed in.
@@ -285,7 +302,7 @@ void hand_peaks_blurred_launch(const float* blurred_planar, int n_crops, int cha
     dim3 g(cdiv(w, 128), h, maps);
     hand_mask_kernel<<<g, 128, 0, stream>>>(blurred_planar, h, w, chan_stride_maps, thre, hb.labels);
     OPB_CUDA(cudaGetLastError());
-    hand_components_launch(blurred_planar, maps, chan_stride_maps, h, w, hb, stream);
+    hand_components_launch(blurred_planar, maps, chan_stride_maps, h, w, hb, nullptr, (size_t)h * w, stream);
 }
 
 // heat: planar (n_crops * chan_stride_maps, h, w) fp32, the first 21 planes of each crop are used
@@ -296,25 +313,39 @@ void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_m
     OPB_CUDA(cudaMemsetAsync(hb.sums, 0, sizeof(double) * (size_t)maps * h * w, stream));
     dim3 g1(cdiv(w, TW), cdiv(h, TH), maps);
     hand_smooth_kernel<<<g1, 256, 0, stream>>>(heat_planar, h, w, chan_stride_maps, gauss_taps_sigma3(), thre,
-                                               hb.labels, smoothed_out);
+                                               hb.labels, smoothed_out, nullptr, (size_t)h * w);
     OPB_CUDA(cudaGetLastError());
-    hand_components_launch(heat_planar, maps, chan_stride_maps, h, w, hb, stream);
+    hand_components_launch(heat_planar, maps, chan_stride_maps, h, w, hb, nullptr, (size_t)h * w, stream);
+}
+
+// ragged batch: crop c is dims[c] x dims[c] (0: no crop, peaks are zero), planes at stride wmax * wmax
+void hand_peaks_ragged_launch(const float* heat_planar, int n_crops, int chan_stride_maps, const int* dims_dev, int wmax,
+                              double thre, HandBuffers hb, cudaStream_t stream) {
+    const int maps = n_crops * 21;
+    OPB_REQUIRE(maps <= 65535, "hand_peaks: too many crops in one batch");
+    const size_t ps = (size_t)wmax * wmax;
+    OPB_CUDA(cudaMemsetAsync(hb.sums, 0, sizeof(double) * (size_t)maps * ps, stream));
+    dim3 g1(cdiv(wmax, TW), cdiv(wmax, TH), maps);
+    hand_smooth_kernel<<<g1, 256, 0, stream>>>(heat_planar, wmax, wmax, chan_stride_maps, gauss_taps_sigma3(), thre,
+                                               hb.labels, nullptr, dims_dev, ps);
+    OPB_CUDA(cudaGetLastError());
+    hand_components_launch(heat_planar, maps, chan_stride_maps, wmax, wmax, hb, dims_dev, ps, stream);
 }
 
 // labels hold the mask (own raster index or -1): components, per-component sums, selection (src/hand.py:68-74)
 static void hand_components_launch(const float* heat_planar, int maps, int chan_stride_maps, int h, int w, HandBuffers hb,
-                                   cudaStream_t stream) {
+                                   const int* dims, size_t ps, cudaStream_t stream) {
     dim3 g2(cdiv(w, 128), h, maps);
     dim3 g0(cdiv(h, 4), maps);
-    hand_runs_kernel<<<g0, 128, 0, stream>>>(hb.labels, h, w);
+    hand_runs_kernel<<<g0, 128, 0, stream>>>(hb.labels, h, w, dims, ps);
     OPB_CUDA(cudaGetLastError());
-    hand_merge_kernel<<<g2, 128, 0, stream>>>(hb.labels, h, w);
+    hand_merge_kernel<<<g2, 128, 0, stream>>>(hb.labels, h, w, dims, ps);
     OPB_CUDA(cudaGetLastError());
-    hand_compress_kernel<<<g2, 128, 0, stream>>>(hb.labels, h, w);
+    hand_compress_kernel<<<g2, 128, 0, stream>>>(hb.labels, h, w, dims, ps);
     OPB_CUDA(cudaGetLastError());
-    hand_flatten_kernel<<<g2, 128, 0, stream>>>(heat_planar, chan_stride_maps, hb.labels, hb.sums, h, w);
+    hand_flatten_kernel<<<g2, 128, 0, stream>>>(heat_planar, chan_stride_maps, hb.labels, hb.sums, h, w, dims, ps);
     OPB_CUDA(cudaGetLastError());
-    hand_select_kernel<<<maps, 1024, 0, stream>>>(heat_planar, chan_stride_maps, hb.labels, hb.sums, h, w, hb.peaks);
+    hand_select_kernel<<<maps, 1024, 0, stream>>>(heat_planar, chan_stride_maps, hb.labels, hb.sums, h, w, hb.peaks, dims, ps);
     OPB_CUDA(cudaGetLastError());
 }
 

@@ -255,7 +255,17 @@ struct Builder {
                 ops.push_back(op);
             }
             // 3x3 / 7x7 layers run patch-resident (conv_patch.cu); 1x1 layers (and OPB_CONV_IMPL=tap) per-tap tiles
-            ConvLaunch* L = (ops[0].ks > 1 && conv_impl == 2) ? conv_pair_plan(ops, bn, net->ctx->num_sms)
+            // Small problems (one 640x480 frame at scale 0.5 gives 4 super-tiles per stage layer) leave most SMs idle and
+            // their latency is the depth of one tile's K loop: halve the N tile so that twice as many CTA pairs share
+            // the work and every UMMA is half as long.
+            int bn_run = bn;
+            if (ops[0].ks > 1 && conv_impl == 2 && bn == 128 && getenv("OPB_NO_SMALL_BN") == nullptr) {
+                long clusters = 0;
+                for (const ConvOp& op : ops)
+                    clusters += (long)((cdiv(op.in.w, 16) * cdiv(op.in.h, 16) * op.in.n + 1) / 2) * (op.cout_pad / 128);
+                if (clusters * 4 <= net->ctx->num_sms) bn_run = 64;
+            }
+            ConvLaunch* L = (ops[0].ks > 1 && conv_impl == 2) ? conv_pair_plan(ops, bn_run, net->ctx->num_sms)
                             : (ops[0].ks > 1 && conv_impl >= 0) ? conv_patch_plan(ops, bn, net->ctx->num_sms, conv_impl)
                                                                 : conv_tc_plan(ops, bn, net->ctx->num_sms);
             plan->launches.push_back(L);

@@ -253,6 +253,31 @@ void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_m
 void hand_peaks_blurred_launch(const float* blurred_planar, int n_crops, int chan_stride_maps, int h, int w, float thre,
                                HandBuffers hb, cudaStream_t stream);
 
+// ---- ragged hand crops: per-slot boxes computed on the device and tap tables for every crop size (prepost.cu, pose.cu)
+struct HandBox {
+    int frame;                // frame of the batch the crop is taken from
+    int x, y, w;              // top-left corner and side length in that frame (util.handDetect, src/util.py:133-201)
+    int left;                 // left hand: the crop is mirrored before the network, x un-mirrored afterwards
+    int valid;                // 0: no box for this slot (no person, missing joints, empty box)
+};
+struct RaggedTables {
+    const uint8_t* slab;      // all tables
+    const unsigned* index;    // [(w * n_scales + s) * 5 + {0: pre first, 1: pre coef, 2: up first, 3: up x weights, 4: up y weights}] byte offsets
+    int n_scales, wmax;
+};
+void preprocess_ragged_launch(const uint8_t* frames, int H, int W, const HandBox* boxes, int n_slots, uint8_t* out, int S,
+                              int scale, const RaggedTables& tabs, cudaStream_t stream);
+void upsample_ragged_launch(const float* const* src, const int* ho, const int* wo, int n_scales, int cstride, int C,
+                            const HandBox* boxes, int n_slots, const RaggedTables& tabs, int wmax, float* scratch,
+                            float* out_planar, cudaStream_t stream);
+void hand_peaks_ragged_launch(const float* heat_planar, int n_crops, int chan_stride_maps, const int* dims_dev, int wmax,
+                              double thre, HandBuffers hb, cudaStream_t stream);
+// person selection + hand boxes from the body results, and the final PoseMat assembly (pose.cu)
+void pose_select_launch(const FramePost* frames_dev, int n_frames, int H, int W, const int* fixed_boxes_dev, double* pose_dev,
+                        HandBox* boxes_dev, int* dims_dev, cudaStream_t stream);
+void pose_finish_launch(const HandBox* boxes_dev, const double* hand_peaks_dev, int n_frames, double* pose_dev,
+                        cudaStream_t stream);
+
 // ---- gaussian taps shared by peaks.cu / hand.cu: scipy.ndimage.gaussian_filter(sigma=3) uses
 // radius int(4*3+0.5) = 12 and weights exp(-x^2/18) / sum (src/body.py:75, src/hand.py:62).  The
 // constants are the exact float64 bit patterns numpy produces (w[d] = weight at distance d), so the

@@ -228,6 +228,146 @@ __global__ void __launch_bounds__(128) upsample_y_blocked_kernel(const __grid_co
             *(float4*)(o + (size_t)i * W) = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
 }
 
+// ---- ragged hand crops (the per-frame caller, srcmx/MotionEstimation.py:163-194): every slot of the batch is a square
+// crop of its own size taken from a frame that is already on the device.  The tap tables of every possible size sit in
+// one slab (built on the host with the same functions as the single-size path); `index` holds, per (size, scale), the
+// byte offsets of {preprocess first, preprocess coef, upsample first, upsample x weights, upsample y weights (1/n_scales
+// folded in)}.
+__device__ __forceinline__ const uint8_t* ragged_table(const RaggedTables& t, int w, int scale, int which) {
+    return t.slab + t.index[((size_t)w * t.n_scales + scale) * 5 + which];
+}
+
+// Hand.__call__'s cv2.resize of the crop (src/hand.py:38) for every slot, reading the crop -- mirrored for left hands,
+// cv2.flip(crop, 1) at srcmx/MotionEstimation.py:191 -- straight from the frame.  Arithmetic as preprocess_kernel.
+__global__ void __launch_bounds__(128) preprocess_ragged_kernel(const uint8_t* __restrict__ frames, int H, int W,
+                                                                const HandBox* __restrict__ boxes, uint8_t* __restrict__ out,
+                                                                int S, int scale, const RaggedTables tabs) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    if (x >= S) return;
+    const HandBox b = boxes[blockIdx.z];
+    uint8_t* o = out + (((size_t)blockIdx.z * S + y) * S + x) * 3;
+    if (!b.valid) {
+        o[0] = o[1] = o[2] = 128;
+        return;
+    }
+    const int w = b.w;
+    const int* xf = (const int*)ragged_table(tabs, w, scale, 0);
+    const short* xc = (const short*)ragged_table(tabs, w, scale, 1);
+    const uint8_t* img = frames + (size_t)b.frame * H * W * 3;
+    const int x0 = xf[x], y0 = xf[y];                            // square crops: one table for both axes
+    int cx[4], wx[4];
+    const short4 xw4 = *(const short4*)(xc + x * 4);
+    wx[0] = xw4.x; wx[1] = xw4.y; wx[2] = xw4.z; wx[3] = xw4.w;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int c = clampi(x0 + j, 0, w - 1);
+        cx[j] = (b.x + (b.left ? w - 1 - c : c)) * 3;
+    }
+    int hor[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const uint8_t* row = img + (size_t)(b.y + clampi(y0 + k, 0, w - 1)) * W * 3;
+        int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint8_t* px = row + cx[j];
+            s0 += (int)__ldg(px) * wx[j];
+            s1 += (int)__ldg(px + 1) * wx[j];
+            s2 += (int)__ldg(px + 2) * wx[j];
+        }
+        hor[k][0] = s0; hor[k][1] = s1; hor[k][2] = s2;
+    }
+    const short4 yw4 = *(const short4*)(xc + y * 4);
+    const int wyi[4] = {yw4.x, yw4.y, yw4.z, yw4.w};
+    const float sc = 1.0f / (2048.0f * 2048.0f);
+    float wyf[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) wyf[k] = __fmul_rn((float)wyi[k], sc);
+    const int nvec = ((S * 3) / 8) * 8;                         // OpenCV: 8-lane SIMD body, scalar tail
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        int r;
+        if (x * 3 + c < nvec) {
+            float acc = __fmul_rn((float)hor[3][c], wyf[3]);
+#pragma unroll
+            for (int k = 2; k >= 0; --k) acc = __fadd_rn(acc, __fmul_rn((float)hor[k][c], wyf[k]));
+            r = __float2int_rn(acc);
+        } else {
+            long long s = 0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) s += (long long)hor[k][c] * (long long)wyi[k];
+            r = (int)((s + (1ll << 21)) >> 22);
+        }
+        o[c] = (uint8_t)clampi(r, 0, 255);
+    }
+}
+
+// x pass of the ragged upsample: tmp[slot][c][r][x] for x < w_slot (row pitch = w_slot), slot stride = C * ho * wmax
+__global__ void upsample_x_ragged_kernel(const float* __restrict__ src, int ho, int wo, int cstride, int C,
+                                         const HandBox* __restrict__ boxes, int scale, const RaggedTables tabs, int wmax,
+                                         float* __restrict__ tmp) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    const int cq_per = (C + 3) >> 2;
+    const int slot = blockIdx.z / cq_per, cq = blockIdx.z - slot * cq_per;
+    const HandBox b = boxes[slot];
+    if (!b.valid || x >= b.w) return;
+    const int w = b.w;
+    const int* xfirst = (const int*)ragged_table(tabs, w, scale, 2);
+    const float* xw = (const float*)ragged_table(tabs, w, scale, 3);
+    const int f = xfirst[x];
+    const float* s = src + (((size_t)slot * ho + r) * wo) * cstride + cq * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < kUpTaps; ++k) {
+        const int col = min(f + k, wo - 1);
+        const float wk = xw[x * kUpTaps + k];
+        const float4 v = *(const float4*)(s + (size_t)col * cstride);
+        acc.x = fmaf(wk, v.x, acc.x);
+        acc.y = fmaf(wk, v.y, acc.y);
+        acc.z = fmaf(wk, v.z, acc.z);
+        acc.w = fmaf(wk, v.w, acc.w);
+    }
+    const float av[4] = {acc.x, acc.y, acc.z, acc.w};
+    float* t = tmp + (size_t)slot * C * ho * wmax;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int ch = cq * 4 + j;
+        if (ch < C) t[((size_t)ch * ho + r) * w + x] = av[j];
+    }
+}
+
+struct UpYRagged {
+    const float* tmp[kMaxScales];     // per scale: [slot][C][ho][w_slot]
+    int ho[kMaxScales];
+    int n_scales;
+};
+// y pass: the chain of upsample_y_kernel with per-slot tables; out[slot][c][y][x], plane pitch w_slot, plane stride ps
+__global__ void upsample_y_ragged_kernel(const __grid_constant__ UpYRagged p, int C, const HandBox* __restrict__ boxes,
+                                         const RaggedTables tabs, int wmax, size_t ps, float* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    const int y = blockIdx.y;
+    const int slot = blockIdx.z / C, c = blockIdx.z - slot * C;
+    const HandBox b = boxes[slot];
+    if (!b.valid || x >= b.w || y >= b.w) return;
+    const int w = b.w;
+    float acc = 0.f;
+    for (int s = 0; s < p.n_scales; ++s) {
+        const int* yfirst = (const int*)ragged_table(tabs, w, s, 2);
+        const float* yw = (const float*)ragged_table(tabs, w, s, 4);
+        const int f = yfirst[y];
+        const int ho = p.ho[s];
+        const float* t = p.tmp[s] + (size_t)slot * C * ho * wmax + (size_t)c * ho * w + x;
+#pragma unroll
+        for (int k = 0; k < kUpTaps; ++k) {
+            const int r = min(f + k, ho - 1);
+            acc = fmaf(yw[y * kUpTaps + k], t[(size_t)r * w], acc);
+        }
+    }
+    out[((size_t)slot * C + c) * ps + (size_t)y * w + x] = acc;
+}
+
 }  // namespace
 
 void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t* out, int h, int w, int hp, int wp,
@@ -236,6 +376,36 @@ void preprocess_launch_batched(const uint8_t* img, int n, int H, int W, uint8_t*
     dim3 grid(cdiv(wp, 128), hp, n);
     preprocess_kernel<<<grid, 128, 0, stream>>>(img, H, W, out, h, w, hp, wp, x_first, x_coef, y_first, y_coef,
                                                 (size_t)H * W * 3, (size_t)hp * wp * 3);
+    OPB_CUDA(cudaGetLastError());
+}
+
+void preprocess_ragged_launch(const uint8_t* frames, int H, int W, const HandBox* boxes, int n_slots, uint8_t* out, int S,
+                              int scale, const RaggedTables& tabs, cudaStream_t stream) {
+    dim3 grid(cdiv(S, 128), S, n_slots);
+    preprocess_ragged_kernel<<<grid, 128, 0, stream>>>(frames, H, W, boxes, out, S, scale, tabs);
+    OPB_CUDA(cudaGetLastError());
+}
+
+// scratch: sum_s n_slots * C * ho_s * wmax floats; out: [n_slots][C] planes at stride wmax * wmax.  The y weights of
+// the tables carry 1/n_scales (the same fold as make_up_tables).
+void upsample_ragged_launch(const float* const* src, const int* ho, const int* wo, int n_scales, int cstride, int C,
+                            const HandBox* boxes, int n_slots, const RaggedTables& tabs, int wmax, float* scratch,
+                            float* out_planar, cudaStream_t stream) {
+    UpYRagged p;
+    memset(&p, 0, sizeof(p));
+    p.n_scales = n_scales;
+    size_t off = 0;
+    for (int s = 0; s < n_scales; ++s) {
+        float* tmp = scratch + off;
+        off += (size_t)n_slots * C * ho[s] * wmax;
+        dim3 grid(cdiv(wmax, 128), ho[s], n_slots * ((C + 3) / 4));
+        upsample_x_ragged_kernel<<<grid, 128, 0, stream>>>(src[s], ho[s], wo[s], cstride, C, boxes, s, tabs, wmax, tmp);
+        OPB_CUDA(cudaGetLastError());
+        p.tmp[s] = tmp;
+        p.ho[s] = ho[s];
+    }
+    dim3 grid(cdiv(wmax, 128), wmax, n_slots * C);
+    upsample_y_ragged_kernel<<<grid, 128, 0, stream>>>(p, C, boxes, tabs, wmax, (size_t)wmax * wmax, out_planar);
     OPB_CUDA(cudaGetLastError());
 }
 
