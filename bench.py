@@ -167,56 +167,57 @@ def extra_hand_c3(local, barrier, max_over_ranks, world):
 
 
 def extra_bodyhand_c4(local, rank, barrier, max_over_ranks, world, streams=2, B=8, F=32, steps=4):
-    """config 4: 720p stream, body (4 scales) + two hand crops (4 scales) per frame.  Random-init weights find no
-    person, so the two hand boxes are fixed 184x184 crops (SURVEY.md 8d C4); left hand mirrored like the caller does."""
+    """config 4: 720p stream, body (4 scales) + two hands (4 scales) per frame through motion.PoseEstimator: the hand
+    crops are cut (the left one mirrored) from the frame already on the device, all 2 * B crops of a batch run as one
+    ragged hand batch, PoseMat (60, 3) per frame is the only result read back.  Random-init weights find no person, so
+    the two hand boxes are fixed 184x184 boxes (SURVEY.md 8d C4) instead of handDetect's."""
     import torch
-    from pytorch_openpose_b200 import Body, Hand
+    from pytorch_openpose_b200 import Body, Hand, motion
     from pytorch_openpose_b200.model import random_checkpoint
     body = Body(random_checkpoint("body", 0), scale_search=SCALES, device=local)
     hand = Hand(random_checkpoint("hand", 0), device=local)
-    bs = [body.net.session() for _ in range(streams)]
-    hs = [hand.net.session() for _ in range(streams)]
+    est = motion.PoseEstimator(body, hand)
+    pairs = est.sessions(streams)
     pool = torch.from_numpy(synth_frames(32, 77 + rank)).pin_memory()
     frames = pool.numpy()
-    boxes = [(700, 300, 184), (400, 300, 184)]
+    boxes = np.tile(np.array([[400, 300, 184], [700, 300, 184]], dtype=np.int32), (B, 1, 1))
 
     def step(i):
         inflight = [False] * streams
         for b in range(F // B):
             si = b % streams
             if inflight[si]:
-                body.collect_batch(bs[si])
-                hand.collect(hs[si])
+                est.collect(pairs[si])
             idx = (i * F + b * B) % 32
-            fr = frames[idx:idx + B]
-            body.submit_batch(fr, bs[si], where=2)
-            crops = np.stack([fr[f, y:y + w, x:x + w] if k == 0 else fr[f, y:y + w, x:x + w][:, ::-1]
-                              for f in range(B) for k, (x, y, w) in enumerate(boxes)])
-            hand.submit(crops, hs[si])
+            est.submit_batch(frames[idx:idx + B], pairs[si], where=2, fixed_boxes=boxes)
             inflight[si] = True
+        out = None
         for si in range(streams):
             if inflight[si]:
-                body.collect_batch(bs[si])
-                hand.collect(hs[si])
+                out = est.collect(pairs[si])
+        return out
 
     for i in range(2):
         step(i)
     barrier()
-    bs[0].mark(0)
+    pairs[0][0].mark(0)
     for i in range(steps):
-        step(2 + i)
-    for s in bs + hs:
-        s.mark(1)
+        out = step(2 + i)
+    for bs, _ in pairs:
+        bs.mark(1)
     torch.cuda.synchronize()
-    ms = max_over_ranks(max(bs[0].elapsed_ms(0, s, 1) for s in bs + hs))
+    ms = max_over_ranks(max(pairs[0][0].elapsed_ms(0, bs, 1) for bs, _ in pairs))
     n = F * steps * world
     peak, _, _ = measured_peaks()
     tf = 6730.4 * F * steps / ms
     return {"value": round(n / (ms * 1e-3), 1), "unit": "frames/s", "ms_per_frame_per_gpu": round(ms / (F * steps), 3),
             "conv_tflops_per_gpu": round(tf, 1),
             "roofline": {"bound": "tensor", "achieved": round(tf, 1), "peak": peak, "unit": "TFLOP/s", "frac": round(tf / peak, 3)},
-            "workload": "body 4-scale + two 184x184 hand crops 4-scale per 720p frame, pinned host frames, host crops "
-                        "(CUDA events over %d frames per GPU)" % (F * steps)}
+            "h2d_bytes_per_frame": H * W * 3, "d2h_bytes_per_frame": 60 * 3 * 8 + 86144,
+            "hand_key_points_found": int((out[:, 18:, 2] > 0).sum()),
+            "workload": "body 4-scale + two 184x184 hand boxes 4-scale per 720p frame, pinned host frames in, PoseMat out; "
+                        "crops, mirroring, resize and the ragged hand batch on the device (CUDA events over %d frames per GPU)"
+                        % (F * steps)}
 
 
 def extra_e2e_decode(local, rank, barrier, max_over_ranks, world, n_frames=256):

@@ -122,6 +122,22 @@ int opb_hand_wait(opb_session* s, double* peaks);
 /* heatmap_avg of the last hand batch: (n_crops, 22, h, w) planar fp32 (src/hand.py:33,57).             */
 int opb_hand_maps(opb_session* s, float* host_heat);
 
+/* ---- the per-frame caller on the device: MotionData_every_frame(mode='bodyhand') ------------------
+ * srcmx/MotionEstimation.py:126-216 for a batch of equally sized frames: body estimation, selection of the
+ * person with the largest left-shoulder x (:144-162), util.handDetect (src/util.py:133-201), both hand
+ * crops taken -- the left one mirrored -- from the frame that is already on the device, Hand on all 2 * n
+ * crops as one ragged batch (every slot keeps its own crop size), key points moved back to frame
+ * coordinates (:185-194).  The only result copied to the host is PoseMat: n x 60 x 3 float64 (rows 0-17
+ * body, 18-38 left hand, 39-59 right hand; zeros = missing).  hand_s must not be used by other calls
+ * while a pose batch is in flight.  fixed_boxes (optional, host, n x 2 x 3 ints: x, y, w of the left and
+ * the right hand box; w <= 0 = none) replaces handDetect's boxes (benchmarks with random weights, which
+ * find no person).  wait returns the first non-OK frame status like opb_body_wait_batch; an empty hand
+ * box (width 0), on which the reference's Hand raises ZeroDivisionError, yields zero rows.            */
+int opb_pose_submit_batch(opb_session* body_s, opb_session* hand_s, const uint8_t* imgs_bgr, int where, int n_frames,
+                          int height, int width, const double* body_scales, int n_body_scales,
+                          const double* hand_scales, int n_hand_scales, const int* fixed_boxes);
+int opb_pose_wait(opb_session* body_s, double* pose_mats, int* frame_status);
+
 /* ---- batched estimators: srcmx/Batch_model.py (the reference author's throughput path) ---------- */
 /* Batch_body.__call__ (srcmx/Batch_model.py:142-204): `frames` = (n, 3, height, width) float32 planar in
  * [0,1] (torchvision ToTensor), one scale g_scale (the reference uses 0.5, :118) with truncating sizes
@@ -179,6 +195,11 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int height, int widt
  * with CUDA events, buffers allocated once.                                                            */
 int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev_paf, int height, int width,
                        int iters, float* ms_per_frame, int* n_candidate, int* n_subset);
+/* srcmx/MotionEstimation.py:141-162 + src/util.py:133-201 on host-provided body results of one frame: body rows of
+ * PoseMat (host_pose180 = 60 x 3, hand rows zero) and the two hand boxes (host_boxes8 = [left, right] x
+ * [x, y, w, valid]) -- the device kernel of the opb_pose_* pipeline, for parity tests.                 */
+int opb_pose_select(opb_context* ctx, const double* host_candidates, int n_candidates, const double* host_subset,
+                    int n_subset, int height, int width, double* host_pose180, int* host_boxes8);
 /* src/hand.py:59-75 on a planar (>=21, h, w) fp32 device map -> 21x3 float64 host array.            */
 int opb_hand_peaks(opb_context* ctx, const float* dev_heat, int height, int width, double thre, double* host_peaks);
 

@@ -50,6 +50,10 @@ SIGNATURES = {
     "opb_body_fetch_frame": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_int]),
     "opb_hand_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_double), c_int]),
     "opb_hand_wait": (c_int, [c_void_p, c_void_p]),
+    "opb_pose_submit_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_double), c_int,
+                                      POINTER(c_double), c_int, c_void_p]),
+    "opb_pose_wait": (c_int, [c_void_p, c_void_p, POINTER(c_int)]),
+    "opb_pose_select": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "opb_body_maps": (c_int, [c_void_p, c_void_p, c_void_p]),
     "opb_hand_maps": (c_int, [c_void_p, c_void_p]),
     "opb_batch_body_submit": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_double]),

@@ -344,6 +344,31 @@ struct opb_session {
     enum { AR_IMG, AR_SCRATCH, AR_HEAT, AR_PAF, AR_LABELS, AR_SUMS, AR_PEAKS, AR_BLUR, AR_COUNT };
     struct Arena { void* p = nullptr; size_t cap = 0; } arena[AR_COUNT];
     uint64_t buffer_gen = 1;         // bumped whenever an arena or a pinned result buffer is reallocated
+    // per-frame caller on the device (opb_pose_*): a hand session carries the tap tables of every crop size, a body
+    // session the per-batch pose / box buffers
+    struct Ragged {
+        DevPool pool;
+        std::vector<double> scales;
+        RaggedTables tabs{};
+        std::vector<int> net_side;   // net input side per scale (the same for every crop size)
+    };
+    std::unique_ptr<Ragged> ragged;
+    struct PoseBuffers {
+        DevPool pool;
+        int frames = 0;
+        double* pose = nullptr;      // [frames][60][3]
+        HandBox* boxes = nullptr;    // [frames][2]
+        int* dims = nullptr;         // [frames][2]
+        int* fixed = nullptr;        // [frames][2][3]
+        double* host = nullptr;      // pinned [frames][60][3]
+        int* fixed_host = nullptr;   // pinned
+        ~PoseBuffers() {
+            if (host) cudaFreeHost(host);
+            if (fixed_host) cudaFreeHost(fixed_host);
+        }
+    };
+    std::unique_ptr<PoseBuffers> pose;
+    opb_session* pose_hand = nullptr;    // hand session of the pose batch in flight
     ~opb_session() {
         plans.clear();
         net_plans.clear();
@@ -899,6 +924,111 @@ static void batch_hand_submit(opb_session* s, const void* crops, bool u8, int wh
     finish_submit(s, fp);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// per-frame caller on the device: MotionData_every_frame(mode='bodyhand'), srcmx/MotionEstimation.py:126-216
+// ------------------------------------------------------------------------------------------------
+// Tap tables for every square crop of side 1..wmax at the hand estimator's scales, built with the same host functions
+// as the single-size path (so a ragged slot is processed exactly like Hand()(crop) would process that crop).
+static void build_ragged_tables(opb_session* hs, const double* scales, int ns, int wmax) {
+    auto r = std::make_unique<opb_session::Ragged>();
+    r->scales.assign(scales, scales + ns);
+    TableSlab slab;
+    std::vector<unsigned> index((size_t)(wmax + 1) * ns * 5, 0u);
+    r->net_side.assign(ns, 0);
+    for (int w = 1; w <= wmax; ++w)
+        for (int s = 0; s < ns; ++s) {
+            const ScaleDims d = scale_dims(w, w, scales[s]);
+            OPB_REQUIRE(d.h == d.w && d.hp == d.h, "hand scales must give square net inputs that are multiples of 8");
+            if (r->net_side[s] == 0) r->net_side[s] = d.hp;
+            OPB_REQUIRE(r->net_side[s] == d.hp, "the net input side must not depend on the crop size (boxsize / crop * crop)");
+            const U8Taps u = make_u8_taps(slab, w, w, d);
+            std::vector<int> fx;
+            std::vector<float> wx;
+            composite_taps(d.wo, d.w, w, fx, wx);
+            std::vector<float> wy(wx);
+            for (auto& v : wy) v = v / (float)ns;                  // same fold as make_up_tables
+            unsigned* e = &index[((size_t)w * ns + s) * 5];
+            e[0] = (unsigned)(size_t)u.xf;
+            e[1] = (unsigned)(size_t)u.xc;
+            e[2] = (unsigned)(size_t)slab.add(fx);
+            e[3] = (unsigned)(size_t)slab.add(wx);
+            e[4] = (unsigned)(size_t)slab.add(wy);
+        }
+    OPB_REQUIRE(slab.host.size() < (1ull << 32), "ragged tables exceed 4 GB");
+    uint8_t* dev = (uint8_t*)r->pool.alloc(slab.host.size());
+    OPB_CUDA(cudaMemcpy(dev, slab.host.data(), slab.host.size(), cudaMemcpyHostToDevice));
+    r->tabs.slab = dev;
+    r->tabs.index = r->pool.upload(index);
+    r->tabs.n_scales = ns;
+    r->tabs.wmax = wmax;
+    hs->ragged = std::move(r);
+}
+
+static void pose_submit(opb_session* bs, opb_session* hs, const uint8_t* imgs, int where, int n, int H, int W,
+                        const double* bscales, int nbs, const double* hscales, int nhs, const int* fixed_boxes) {
+    OPB_REQUIRE(bs->net->kind == OPB_NET_BODY && hs->net->kind == OPB_NET_HAND, "pose: a body session and a hand session");
+    OPB_REQUIRE(bs->net->ctx == hs->net->ctx, "pose: both networks must live on the same context");
+    OPB_REQUIRE(n >= 1 && n <= 64, "1..64 frames per batch");
+    OPB_CUDA(cudaSetDevice(bs->net->ctx->device));
+    const int wmax = std::min(H, W), slots = 2 * n;
+    if (!hs->ragged || hs->ragged->tabs.wmax < wmax || hs->ragged->scales != std::vector<double>(hscales, hscales + nhs)) {
+        OPB_CUDA(cudaStreamSynchronize(bs->stream));
+        build_ragged_tables(hs, hscales, nhs, wmax);
+    }
+    const int tw = hs->ragged->tabs.wmax;                       // plane pitch of the ragged buffers
+    if (!bs->pose || bs->pose->frames < n) {
+        OPB_CUDA(cudaStreamSynchronize(bs->stream));
+        auto pb = std::make_unique<opb_session::PoseBuffers>();
+        pb->frames = n;
+        pb->pose = pb->pool.alloc_t<double>((size_t)n * 180);
+        pb->boxes = pb->pool.alloc_t<HandBox>((size_t)n * 2);
+        pb->dims = pb->pool.alloc_t<int>((size_t)n * 2);
+        pb->fixed = pb->pool.alloc_t<int>((size_t)n * 6);
+        OPB_CUDA(cudaMallocHost((void**)&pb->host, (size_t)n * 180 * sizeof(double)));
+        OPB_CUDA(cudaMallocHost((void**)&pb->fixed_host, (size_t)n * 6 * sizeof(int)));
+        bs->pose = std::move(pb);
+    }
+    // body part: as opb_body_submit_batch
+    FramePlan* fp = get_plan(bs, n, H, W, bscales, nbs);
+    ensure_host(bs, n, 0);
+    bs->active = fp;
+    bs->n_frames = n;
+    bs->pose_hand = hs;
+    cudaStream_t st = bs->stream;
+    upload_image(bs, fp, imgs, where, (size_t)n * H * W * 3);
+    run_front(bs, fp, n, H, W);
+    body_post_enqueue(bs, fp, n, H, W);
+    // hand part on the same stream, with the hand session's CNN plan and work buffers (sized for the largest crop)
+    OPB_CUDA(cudaStreamSynchronize(hs->stream));               // nothing of the hand session's own stream may still use them
+    FramePlan* hp = get_plan(hs, slots, tw, tw, hscales, nhs);
+    hs->active = hp;
+    hs->hand_crops = slots;
+    int* fixed_dev = nullptr;
+    if (fixed_boxes) {
+        OPB_CUDA(cudaStreamSynchronize(st));                   // the pinned copy of the previous batch's boxes is free
+        memcpy(bs->pose->fixed_host, fixed_boxes, (size_t)n * 6 * sizeof(int));
+        OPB_CUDA(cudaMemcpyAsync(bs->pose->fixed, bs->pose->fixed_host, (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+        fixed_dev = bs->pose->fixed;
+    }
+    pose_select_launch(fp->post_dev, n, H, W, fixed_dev, bs->pose->pose, bs->pose->boxes, bs->pose->dims, st);
+    const opb_session::Ragged& rg = *hs->ragged;
+    const float* src[kMaxScales];
+    int ho[kMaxScales], wo[kMaxScales];
+    for (int s = 0; s < nhs; ++s) {
+        preprocess_ragged_launch(fp->d_img, H, W, bs->pose->boxes, slots, hp->net->in_u8[s], rg.net_side[s], s, rg.tabs, st);
+        src[s] = hp->net->out_heat[s];
+        ho[s] = wo[s] = rg.net_side[s] / 8;
+    }
+    hp->net->run(st, nullptr);
+    upsample_ragged_launch(src, ho, wo, nhs, 24, 22, bs->pose->boxes, slots, rg.tabs, tw, hp->up_scratch, hp->heat_avg, st);
+    hand_peaks_ragged_launch(hp->heat_avg, slots, 22, bs->pose->dims, tw, 0.03, hp->hb, st);      // thre, src/hand.py:31
+    pose_finish_launch(bs->pose->boxes, hp->hb.peaks, n, bs->pose->pose, st);
+    OPB_CUDA(cudaMemcpyAsync(bs->pose->host, bs->pose->pose, (size_t)n * 180 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    OPB_CUDA(cudaEventRecord(bs->done, st));
+    bs->net->ctx->launches += fp->launches_per_frame + nhs + hp->net->kernel_launches + (nhs + 1) + 6 + 2;
+}
+
 }  // namespace opb
 
 // ================================================================================================
@@ -1184,6 +1314,41 @@ int opb_batch_maps(opb_session* s, float* host_blurred_heat) {
     });
 }
 
+/* ---- per-frame caller on the device ------------------------------------------------------------------------------ */
+int opb_pose_submit_batch(opb_session* body_s, opb_session* hand_s, const uint8_t* imgs, int where, int n_frames, int H,
+                          int W, const double* body_scales, int n_body_scales, const double* hand_scales,
+                          int n_hand_scales, const int* fixed_boxes) {
+    return guarded([&] {
+        OPB_REQUIRE(body_s && hand_s && imgs && body_scales && hand_scales, "null argument");
+        OPB_REQUIRE(n_hand_scales >= 1 && n_hand_scales <= kMaxScales, "1..8 hand scales");
+        pose_submit(body_s, hand_s, imgs, where, n_frames, H, W, body_scales, n_body_scales, hand_scales, n_hand_scales,
+                    fixed_boxes);
+    });
+}
+int opb_pose_wait(opb_session* body_s, double* pose_mats, int* frame_status) {
+    int rc = OPB_OK;
+    int g = guarded([&] {
+        OPB_REQUIRE(body_s && pose_mats && body_s->pose && body_s->active, "no pose batch in flight");
+        // body results first: they report the overflow / IndexError conditions of every frame
+        std::vector<int> st(body_s->n_frames);
+        OPB_CUDA(cudaEventSynchronize(body_s->done));
+        for (int f = 0; f < body_s->n_frames; ++f) {
+            const HostResults* h = body_s->host + f;
+            const int status = h->counts[21];
+            const FramePost& bp = body_s->active->post[f];
+            if (h->counts[0] > bp.pb.capacity || (status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow)))
+                throw Error(OPB_ERR_CAPACITY, "a frame overflowed the body result buffers: use opb_body_submit_batch for it");
+            st[f] = (status & kStIndexError) ? OPB_ERR_SUBSET_INDEX : OPB_OK;
+            if (frame_status) frame_status[f] = st[f];
+            if (st[f] != OPB_OK && rc == OPB_OK) rc = st[f];
+        }
+        memcpy(pose_mats, body_s->pose->host, (size_t)body_s->n_frames * 180 * sizeof(double));
+        if (rc == OPB_ERR_SUBSET_INDEX)
+            set_last_error("list assignment index out of range (three subset rows match one connection, src/body.py:173)");
+    });
+    return g != OPB_OK ? g : rc;
+}
+
 int opb_hand_submit(opb_session* s, const uint8_t* crops, int img_is_device, int n, int H, int W, const double* scales, int ns) {
     return guarded([&] {
         OPB_REQUIRE(s && crops && scales, "null argument");
@@ -1411,6 +1576,40 @@ int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev
         if (n_subset) *n_subset = ns;
         cudaEventDestroy(e0);
         cudaEventDestroy(e1);
+    });
+}
+
+/* stage-level: person selection + hand boxes (pose.cu) on host-provided body results */
+int opb_pose_select(opb_context* ctx, const double* host_candidates, int n_candidates, const double* host_subset, int n_subset,
+                    int H, int W, double* host_pose180, int* host_boxes8) {
+    return guarded([&] {
+        OPB_REQUIRE(ctx && host_pose180 && host_boxes8 && n_candidates >= 0 && n_subset >= 0, "bad arguments");
+        OPB_CUDA(cudaSetDevice(ctx->device));
+        StagePost sp;
+        sp.create(std::max(n_candidates, 1), 1, 1, std::max(n_subset, 1), nullptr, ctx->stream);
+        int pb19[19];
+        for (int i = 0; i < 19; ++i) pb19[i] = n_candidates;       // only the total is read
+        OPB_CUDA(cudaMemcpyAsync(sp.host.pb.part_begin, pb19, sizeof(pb19), cudaMemcpyHostToDevice, ctx->stream));
+        OPB_CUDA(cudaMemcpyAsync(sp.host.lb.subset_count, &n_subset, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+        if (n_candidates)
+            OPB_CUDA(cudaMemcpyAsync(sp.host.pb.candidates, host_candidates, (size_t)n_candidates * 32, cudaMemcpyHostToDevice, ctx->stream));
+        if (n_subset)
+            OPB_CUDA(cudaMemcpyAsync(sp.host.lb.subset, host_subset, (size_t)n_subset * 160, cudaMemcpyHostToDevice, ctx->stream));
+        DevPool pool;
+        double* pose = pool.alloc_t<double>(180);
+        HandBox* boxes = pool.alloc_t<HandBox>(2);
+        int* dims = pool.alloc_t<int>(2);
+        pose_select_launch(sp.dev, 1, H, W, nullptr, pose, boxes, dims, ctx->stream);
+        HandBox hb[2];
+        OPB_CUDA(cudaMemcpyAsync(host_pose180, pose, 180 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaMemcpyAsync(hb, boxes, sizeof(hb), cudaMemcpyDeviceToHost, ctx->stream));
+        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+        for (int k = 0; k < 2; ++k) {
+            host_boxes8[k * 4 + 0] = hb[k].x;
+            host_boxes8[k * 4 + 1] = hb[k].y;
+            host_boxes8[k * 4 + 2] = hb[k].w;
+            host_boxes8[k * 4 + 3] = hb[k].valid;
+        }
     });
 }
 

@@ -39,7 +39,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 __global__ void __launch_bounds__(256) hand_smooth_kernel(const float* __restrict__ heat, int h, int w, int chan_stride_maps,
                                                           const GaussTaps taps, double thre, int* __restrict__ labels,
                                                           double* __restrict__ smoothed_out, const int* __restrict__ dims,
-                                                          size_t ps) {
+                                                          size_t ps, double* __restrict__ sums) {
     __shared__ double raw[RAW_H][RAW_W];
     __shared__ double ver[TH][RAW_W];
     const int m = blockIdx.z;                                   // map index = crop * 21 + part
@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(256) hand_smooth_kernel(const float* __restric
             acc = __dadd_rn(acc, __dmul_rn(__dadd_rn(ver[ty][tx + R - d], ver[ty][tx + R + d]), taps.w[d]));
         const size_t idx = (size_t)m * ps + (size_t)y * w + x;
         labels[idx] = acc > thre ? y * w + x : -1;
+        sums[idx] = 0.0;                                        // per-root sums are accumulated by hand_flatten_kernel
         if (smoothed_out) smoothed_out[idx] = acc;
     }
 }
@@ -278,13 +279,14 @@ __global__ void __launch_bounds__(1024) hand_select_kernel(const float* __restri
 
 // Batch_hand (srcmx/Batch_model.py:391-392): the map is already blurred; mask = value > thre, compared in float32
 __global__ void hand_mask_kernel(const float* __restrict__ heat, int h, int w, int chan_stride_maps, float thre,
-                                 int* __restrict__ labels) {
+                                 int* __restrict__ labels, double* __restrict__ sums) {
     const int m = blockIdx.z;
     const int crop = m / 21, part = m - crop * 21;
     const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= w) return;
     const float v = __ldg(heat + ((size_t)crop * chan_stride_maps + part) * h * w + (size_t)y * w + x);
     labels[(size_t)m * h * w + (size_t)y * w + x] = v > thre ? y * w + x : -1;
+    sums[(size_t)m * h * w + (size_t)y * w + x] = 0.0;
 }
 
 }  // namespace
@@ -298,9 +300,8 @@ void hand_peaks_blurred_launch(const float* blurred_planar, int n_crops, int cha
                                HandBuffers hb, cudaStream_t stream) {
     const int maps = n_crops * 21;
     OPB_REQUIRE(maps <= 65535, "hand_peaks: too many crops in one batch");
-    OPB_CUDA(cudaMemsetAsync(hb.sums, 0, sizeof(double) * (size_t)maps * h * w, stream));
     dim3 g(cdiv(w, 128), h, maps);
-    hand_mask_kernel<<<g, 128, 0, stream>>>(blurred_planar, h, w, chan_stride_maps, thre, hb.labels);
+    hand_mask_kernel<<<g, 128, 0, stream>>>(blurred_planar, h, w, chan_stride_maps, thre, hb.labels, hb.sums);
     OPB_CUDA(cudaGetLastError());
     hand_components_launch(blurred_planar, maps, chan_stride_maps, h, w, hb, nullptr, (size_t)h * w, stream);
 }
@@ -310,10 +311,9 @@ void hand_peaks_launch2(const float* heat_planar, int n_crops, int chan_stride_m
                         HandBuffers hb, double* smoothed_out, cudaStream_t stream) {
     const int maps = n_crops * 21;
     OPB_REQUIRE(maps <= 65535, "hand_peaks: too many crops in one batch");
-    OPB_CUDA(cudaMemsetAsync(hb.sums, 0, sizeof(double) * (size_t)maps * h * w, stream));
     dim3 g1(cdiv(w, TW), cdiv(h, TH), maps);
     hand_smooth_kernel<<<g1, 256, 0, stream>>>(heat_planar, h, w, chan_stride_maps, gauss_taps_sigma3(), thre,
-                                               hb.labels, smoothed_out, nullptr, (size_t)h * w);
+                                               hb.labels, smoothed_out, nullptr, (size_t)h * w, hb.sums);
     OPB_CUDA(cudaGetLastError());
     hand_components_launch(heat_planar, maps, chan_stride_maps, h, w, hb, nullptr, (size_t)h * w, stream);
 }
@@ -324,10 +324,9 @@ void hand_peaks_ragged_launch(const float* heat_planar, int n_crops, int chan_st
     const int maps = n_crops * 21;
     OPB_REQUIRE(maps <= 65535, "hand_peaks: too many crops in one batch");
     const size_t ps = (size_t)wmax * wmax;
-    OPB_CUDA(cudaMemsetAsync(hb.sums, 0, sizeof(double) * (size_t)maps * ps, stream));
     dim3 g1(cdiv(wmax, TW), cdiv(wmax, TH), maps);
     hand_smooth_kernel<<<g1, 256, 0, stream>>>(heat_planar, wmax, wmax, chan_stride_maps, gauss_taps_sigma3(), thre,
-                                               hb.labels, nullptr, dims_dev, ps);
+                                               hb.labels, nullptr, dims_dev, ps, hb.sums);
     OPB_CUDA(cudaGetLastError());
     hand_components_launch(heat_planar, maps, chan_stride_maps, wmax, wmax, hb, dims_dev, ps, stream);
 }

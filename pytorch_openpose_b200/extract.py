@@ -242,7 +242,12 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
     outname = os.path.split(outpath)[1]
     done = 0
     hand_pool = None
-    if mode == "bodyhand" and pipelined and hasattr(hand_estimation, "submit") and hasattr(hand_estimation, "net"):
+    native_hand = mode == "bodyhand" and pipelined and hasattr(hand_estimation, "submit") and hasattr(hand_estimation, "net")
+    if native_hand and type(body_estimation).__name__ == "Body" and os.environ.get("OPB_HOST_HANDS") is None:
+        # both estimators are this package's: person selection, hand boxes, crops and the hand network stay on the
+        # device, PoseMat is the only thing that comes back (motion.PoseEstimator)
+        return _extract_bodyhand_on_device(src, outpath, body_estimation, hand_estimation, sessions, pinned, log, stats)
+    if native_hand:
         hand_pool = _HandPool(hand_estimation, 4)
 
     def finish(frames, first, results):
@@ -301,6 +306,56 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
             finish(frames, first, [body_estimation(frames[f]) for f in range(len(frames))])
     if hand_pool is not None:
         hand_pool.drain()
+    joblib.dump(mat, outpath)
+    log("%s is saved!" % outpath)
+    return mat
+
+
+def _extract_bodyhand_on_device(src, outpath, body_estimation, hand_estimation, sessions, pinned, log, stats):
+    """mode='bodyhand' with the per-frame caller on the device: batches of frames in flight on `sessions` (body, hand)
+    session pairs; every collect returns PoseMat rows for its batch."""
+    import time
+    import joblib
+    from .motion import PoseEstimator
+    est = body_estimation.__dict__.setdefault("_pose_estimator", None)
+    if est is None or est.hand is not hand_estimation:
+        est = body_estimation.__dict__["_pose_estimator"] = PoseEstimator(body_estimation, hand_estimation)
+    pairs = est.sessions(sessions)
+    mat = np.zeros((src.count, 60, 3))
+    outname = os.path.split(outpath)[1]
+    clock = {"decode_wait": 0.0, "submit": 0.0, "collect_wait": 0.0, "records": 0.0}
+    pending = []
+
+    def retire():
+        pair, first, nv = pending.pop(0)
+        t = time.perf_counter()
+        pose = est.collect(pair)
+        clock["collect_wait"] += time.perf_counter() - t
+        hi = min(first + nv, len(mat))
+        if hi > first:
+            mat[first:hi] = pose[:hi - first]
+        if first % 100 < len(pose):
+            log("%s-%d/%d" % (outname, first, src.count))
+
+    it = iter(src)
+    while True:
+        t = time.perf_counter()
+        item = next(it, None)
+        clock["decode_wait"] += time.perf_counter() - t
+        if item is None:
+            break
+        frames, first, n_valid = item
+        if len(pending) == len(pairs):
+            retire()
+        pair = next(c for c in pairs if all(c is not p[0] for p in pending))
+        t = time.perf_counter()
+        est.submit_batch(frames, pair, where=2 if pinned else 0)
+        clock["submit"] += time.perf_counter() - t
+        pending.append((pair, first, n_valid))
+    while pending:
+        retire()
+    if stats is not None:
+        stats.update(clock)
     joblib.dump(mat, outpath)
     log("%s is saved!" % outpath)
     return mat
