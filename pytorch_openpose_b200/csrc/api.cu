@@ -300,9 +300,8 @@ static void alloc_body_post(DevPool& pool, FramePost& fp, int* counters, FrameRe
     fp.lb.conn_count = counters + 65;
     fp.lb.conn = pool.alloc_t<double>((size_t)19 * conn_cap * 5, true);
     fp.lb.subset = pool.alloc_t<double>((size_t)subset_cap * 20, true);
-    fp.lb.rows_global = subset_cap > kSubsetRowsShared ? pool.alloc_t<double>((size_t)subset_cap * 20) : nullptr;
+    fp.lb.rows_global = subset_cap > kSubsetRowsShared ? pool.alloc_t<double>((size_t)subset_cap * kSubsetRowStride) : nullptr;
     fp.lb.order = pool.alloc_t<int>((size_t)19 * pair_cap);
-    fp.lb.used = pool.alloc_t<unsigned char>((size_t)19 * 2 * peak_cap);
     fp.result = result;
 }
 
@@ -554,7 +553,7 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
                             tiny ? 64 : kPeakCapacity, tiny ? 64 : kPairCapacity, tiny ? 16 : kConnCapacity,
                             tiny ? 4 : kSubsetCapacity);
         upload_post_table(fp.get(), s->stream);
-        fp->launches_per_frame += 7 + (fp->fused_ok ? 0 : n_scales + 1);
+        fp->launches_per_frame += 8 + (fp->fused_ok ? 0 : n_scales + 1);   // bounds, peaks, order, score, sort, match, assemble, pack
     } else {
         fp->launches_per_frame += (n_scales + 1) + 6 + (mode >= 1);
     }
@@ -685,16 +684,17 @@ static void body_post_range(opb_session* s, FramePlan* fp, int f0, int nf, int H
         heat.planes_per_frame = 19;
     }
     paf.comp = composite_of(fp, true, 40);
-    int peak_cap = 0, subset_cap = 0;
+    int peak_cap = 0, subset_cap = 0, pair_cap = 0;
     for (int f = f0; f < f0 + nf; ++f) {
         peak_cap = std::max(peak_cap, fp->post[f].pb.capacity);
         subset_cap = std::max(subset_cap, fp->post[f].lb.subset_capacity);
+        pair_cap = std::max(pair_cap, fp->post[f].lb.pair_capacity);
     }
     find_peaks_launch(heat, nf, H, W, 18, mode, 0.1, fp->post_dev + f0, nullptr, fp->tile_mask, st);      // thre1: src/body.py:30, Batch_model.py:121
     s->prof.mark(st, "find_peaks");
     order_peaks_launch(fp->post_dev + f0, nf, peak_cap, 18, st);
     s->prof.mark(st, "order_peaks");
-    paf_group_launch(paf, nf, H, W, fp->post_dev + f0, 0.05, subset_cap, st);               // thre2, src/body.py:31
+    paf_group_launch(paf, nf, H, W, fp->post_dev + f0, 0.05, subset_cap, pair_cap, peak_cap, st);               // thre2, src/body.py:31
     s->prof.mark(st, "paf_group");
     pack_results_launch(fp->post_dev + f0, nf, st);
     OPB_CUDA(cudaMemcpyAsync(s->host + f0, fp->results_dev + f0, (size_t)nf * sizeof(FrameResults), cudaMemcpyDeviceToHost, st));
@@ -712,7 +712,7 @@ static bool grow_and_redo(opb_session* s, FramePlan* fp, int f, int appended, in
     FramePost& bp = fp->post[f];
     int peak_cap = bp.pb.capacity, pair_cap = bp.lb.pair_capacity, conn_cap = bp.lb.conn_capacity;
     int subset_cap = bp.lb.subset_capacity;
-    constexpr int kMaxPeaks = 1 << 18, kMaxPairs = 1 << 20, kMaxConn = 1 << 16, kMaxSubset = 1 << 16;
+    constexpr int kMaxPeaks = 1 << 18, kMaxPairs = 1 << 20, kMaxConn = 1 << 16, kMaxSubset = 1 << 16;      // 2^18 peaks: 64 KB of bitmaps in limb matching
     bool grew = false;
     if (appended > peak_cap && peak_cap < kMaxPeaks) {
         while (peak_cap < appended && peak_cap < kMaxPeaks) peak_cap *= 4;
@@ -1509,19 +1509,26 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int H, int W, const 
         int max_part = 1;
         for (int p = 0; p < 18; ++p) max_part = std::max(max_part, host_part_begin19[p + 1] - host_part_begin19[p]);
         const int conn_cap = conn_capacity > 0 ? conn_capacity : std::max(1, max_part);
-        StagePost sp;
-        sp.create(std::max(total, 1), kPairCapacity, conn_cap, std::max(subset_capacity, 1), const_cast<double*>(dev_candidates),
-                  ctx->stream);
-        OPB_CUDA(cudaMemcpyAsync(sp.host.pb.part_begin, host_part_begin19, 19 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
         MapSource src;
         src.planar = dev_paf;
         src.planes_per_frame = 38;
-        paf_group_launch(src, 1, H, W, sp.dev, thre2, sp.host.lb.subset_capacity, ctx->stream);
-        ctx->launches += 3;
         int status[4], count = 0;
-        OPB_CUDA(cudaMemcpyAsync(status, sp.host.lb.status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
-        OPB_CUDA(cudaMemcpyAsync(&count, sp.host.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-        OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+        std::unique_ptr<StagePost> spp;
+        // the survivor lists grow on demand, like in the frame path (the reference has no limit)
+        for (int pair_cap = kPairCapacity;; pair_cap *= 4) {
+            spp = std::make_unique<StagePost>();
+            spp->create(std::max(total, 1), pair_cap, conn_cap, std::max(subset_capacity, 1), const_cast<double*>(dev_candidates),
+                        ctx->stream);
+            OPB_CUDA(cudaMemcpyAsync(spp->host.pb.part_begin, host_part_begin19, 19 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+            paf_group_launch(src, 1, H, W, spp->dev, thre2, spp->host.lb.subset_capacity, spp->host.lb.pair_capacity,
+                             spp->host.lb.max_part, ctx->stream);
+            ctx->launches += 4;
+            OPB_CUDA(cudaMemcpyAsync(status, spp->host.lb.status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
+            OPB_CUDA(cudaMemcpyAsync(&count, spp->host.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            OPB_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (!(status[0] & kStPairOverflow) || pair_cap >= (1 << 20)) break;
+        }
+        StagePost& sp = *spp;
         if (status[0] & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))
             throw Error(OPB_ERR_CAPACITY, "limb / person buffers overflowed (status " + std::to_string(status[0]) + ")");
         *n_subset = count;
@@ -1558,7 +1565,7 @@ int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev
             sp.clear(ctx->stream);
             find_peaks_launch(heat, 1, H, W, 18, 0, 0.1, sp.dev, nullptr, nullptr, ctx->stream);
             order_peaks_launch(sp.dev, 1, sp.host.pb.capacity, 18, ctx->stream);
-            paf_group_launch(paf, 1, H, W, sp.dev, 0.05, sp.host.lb.subset_capacity, ctx->stream);
+            paf_group_launch(paf, 1, H, W, sp.dev, 0.05, sp.host.lb.subset_capacity, sp.host.lb.pair_capacity, sp.host.lb.max_part, ctx->stream);
         };
         for (int i = 0; i < 3; ++i) once();
         OPB_CUDA(cudaEventRecord(e0, ctx->stream));
@@ -1568,7 +1575,7 @@ int opb_bench_grouping(opb_context* ctx, const float* dev_heat, const float* dev
         float ms = 0.f;
         OPB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
         *ms_per_frame = ms / (float)iters;
-        ctx->launches += 5 * (iters + 3);
+        ctx->launches += 6 * (iters + 3);
         int pb19[19], ns = 0;
         OPB_CUDA(cudaMemcpy(pb19, sp.host.pb.part_begin, sizeof(pb19), cudaMemcpyDeviceToHost));
         OPB_CUDA(cudaMemcpy(&ns, sp.host.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost));

@@ -187,15 +187,15 @@ struct LimbBuffers {
     double* conn;             // [19][conn_capacity][5]  (idA, idB, score, i, j)
     int* conn_count;          // [19]
     double* subset;           // [subset_capacity][20]
-    double* rows_global;      // [subset_capacity][20] assembly work rows when they do not fit shared memory, else null
+    double* rows_global;      // [subset_capacity][kSubsetRowStride] assembly work rows when they do not fit shared memory, else null
     int* subset_count;        // [1] rows after pruning
     int* status;              // [4]: bit flags (overflow / IndexError edge), rows before pruning, ...
     int* order;               // [19][pair_capacity] sorted order of the survivors
-    unsigned char* used;      // [19][2][max_part]
     int pair_capacity, conn_capacity, subset_capacity, max_part;
 };
 constexpr int kStPairOverflow = 1, kStConnOverflow = 2, kStSubsetOverflow = 4, kStIndexError = 8;
 constexpr int kSubsetRowsShared = 1024;   // assembly rows kept in shared memory up to this many
+constexpr int kSubsetRowStride = 21;      // doubles between work rows (20 used)
 
 // everything the post-processing kernels need for ONE frame of a batch; the kernels take a device array of these
 // and pick theirs by block index, so a batch is one launch per stage
@@ -237,8 +237,9 @@ bool composite_fits_fused(const std::vector<std::vector<int>>& xf, const std::ve
 void order_peaks_launch(const FramePost* frames_dev, int n_frames, int max_capacity, int parts, cudaStream_t stream);
 void blur5_planar_launch(const float* maps_planar, float* out_planar, int n_maps, int H, int W, cudaStream_t stream);
 
+// subset_capacity / pair_capacity / max_part: the largest of the launch's frames (grid and shared-memory sizing)
 void paf_group_launch(const MapSource& paf, int n_frames, int H, int W, const FramePost* frames_dev, double thre2,
-                      int subset_capacity, cudaStream_t stream);
+                      int subset_capacity, int pair_capacity, int max_part, cudaStream_t stream);
 // copies counts + the first rows of candidates / subsets of every frame into FramePost::result
 void pack_results_launch(const FramePost* frames_dev, int n_frames, cudaStream_t stream);
 

@@ -7,8 +7,9 @@
 //                     mid_num=10 nearest-pixel samples of the limb's two PAF channels (np.linspace + round
 //                     half-even), lane 0 folds them in index order (Python's builtin sum), applies the distance
 //                     prior min(0.5*H/norm-1, 0) and both criteria, and appends survivors to the limb's list.
-//   limb_match_kernel one CTA per limb: rank-sorts survivors by (score desc, i asc, j asc) == Python's stable
-//                     sorted(..., reverse=True) over the (i, j) loop order, then walks them greedily.
+//   limb_sort_kernel  segmented sort: every (frame, limb) segment of survivors is ordered by (score desc, i asc, j asc)
+//                     == Python's stable sorted(..., reverse=True) over the (i, j) loop order, in one launch.
+//   limb_match_kernel one CTA per (frame, limb): the greedy walk over the sorted survivors.
 //   assemble_kernel   one warp: the reference's sequential row merge (found==1 / found==2 / new row, k < 17),
 //                     rows kept in shared memory (in a global work buffer beyond 1024 rows), row search parallel
 //                     over lanes, then pruning.
@@ -110,82 +111,118 @@ __device__ __forceinline__ bool cand_before(double s1, long long o1, double s2, 
     return s1 > s2 || (s1 == s2 && o1 < o2);
 }
 
-__global__ void __launch_bounds__(256) limb_match_kernel(const FramePost* __restrict__ frames) {
+// Segmented sort of the survivors: one launch orders every (frame, limb) segment.  Each CTA ranks 256 survivors of its
+// segment against the whole segment (keys are unique in (i, j), so the ranks are a permutation); the segment's CTAs
+// work in parallel, so a crowded limb is spread over the GPU instead of one SM.
+__global__ void __launch_bounds__(256) limb_sort_kernel(const FramePost* __restrict__ frames) {
     __shared__ double s_score[256];
     __shared__ long long s_ord[256];
+    const int k = blockIdx.y;
+    const FramePost& fr = frames[blockIdx.z];
+    const LimbBuffers& lb = fr.lb;
+    const int n = min(lb.cand_count[k], lb.pair_capacity);
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if ((int)(blockIdx.x * blockDim.x) >= n) return;
+    const int* __restrict__ part_begin = fr.pb.part_begin;
+    const int pb = c_limb_b[k];
+    const int nB = part_begin[pb + 1] - part_begin[pb];
+    const double* sc = lb.cand_score + (size_t)k * lb.pair_capacity;
+    const int* ij = lb.cand_ij + (size_t)k * lb.pair_capacity * 2;
+    int* ord = lb.order + (size_t)k * lb.pair_capacity;
+    const double my_s = c < n ? sc[c] : 0.0;
+    const long long my_o = c < n ? (long long)ij[2 * c] * nB + ij[2 * c + 1] : 0;
+    int rank = 0;
+    for (int base = 0; base < n; base += 256) {
+        const int t = base + threadIdx.x;
+        if (t < n) {
+            s_score[threadIdx.x] = sc[t];
+            s_ord[threadIdx.x] = (long long)ij[2 * t] * nB + ij[2 * t + 1];
+        }
+        __syncthreads();
+        const int m = min(256, n - base);
+        if (c < n)
+            for (int q = 0; q < m; ++q) rank += cand_before(s_score[q], s_ord[q], my_s, my_o);
+        __syncthreads();
+    }
+    if (c < n) ord[rank] = c;
+}
+
+// greedy walk over the sorted survivors (src/body.py:143-150) -- sequential by definition: one thread walks, the CTA
+// stages the sorted entries through shared memory in chunks (coalesced gathers instead of dependent global loads) and
+// the "already used" sets are bitmaps in shared memory
+__global__ void __launch_bounds__(256) limb_match_kernel(const FramePost* __restrict__ frames) {
+    extern __shared__ unsigned used_bits[];          // [2][ceil(max_part / 32)]
+    constexpr int CH = 1024;
+    __shared__ int s_i[CH], s_j[CH], s_c[CH];
+    __shared__ int s_count, s_done;
     const int k = blockIdx.x;
     const FramePost& fr = frames[blockIdx.y];
     const int* __restrict__ part_begin = fr.pb.part_begin;
     const LimbBuffers& lb = fr.lb;
-    const int max_part = lb.max_part;
     const int pa = c_limb_a[k], pb = c_limb_b[k];
     const int a0 = part_begin[pa], nA = part_begin[pa + 1] - a0;
     const int b0 = part_begin[pb], nB = part_begin[pb + 1] - b0;
     const int n = min(lb.cand_count[k], lb.pair_capacity);
     const double* sc = lb.cand_score + (size_t)k * lb.pair_capacity;
     const int* ij = lb.cand_ij + (size_t)k * lb.pair_capacity * 2;
-    int* ord = lb.order + (size_t)k * lb.pair_capacity;
-    unsigned char* usedA = lb.used + (size_t)k * 2 * max_part;
-    unsigned char* usedB = usedA + max_part;
+    const int* ord = lb.order + (size_t)k * lb.pair_capacity;
+    const int words = (lb.max_part + 31) / 32;
+    unsigned* usedA = used_bits;
+    unsigned* usedB = used_bits + words;
 
     if (threadIdx.x == 0) lb.conn_count[k] = (nA == 0 || nB == 0) ? -1 : 0;   // -1: limb in special_k
     if (nA == 0 || nB == 0 || n == 0) return;
-
-    for (int t = threadIdx.x; t < nA; t += blockDim.x) usedA[t] = 0;
-    for (int t = threadIdx.x; t < nB; t += blockDim.x) usedB[t] = 0;
-
-    // rank sort (candidates are unique in (i, j), so ranks are a permutation)
-    for (int base_i = 0; base_i < n; base_i += blockDim.x) {
-        const int c = base_i + threadIdx.x;
-        const double my_s = c < n ? sc[c] : 0.0;
-        const long long my_o = c < n ? (long long)ij[2 * c] * nB + ij[2 * c + 1] : 0;
-        int rank = 0;
-        for (int base = 0; base < n; base += 256) {
-            const int t = base + threadIdx.x;
-            if (t < n) {
-                s_score[threadIdx.x] = sc[t];
-                s_ord[threadIdx.x] = (long long)ij[2 * t] * nB + ij[2 * t + 1];
-            }
-            __syncthreads();
-            const int m = min(256, n - base);
-            if (c < n)
-                for (int q = 0; q < m; ++q) rank += cand_before(s_score[q], s_ord[q], my_s, my_o);
-            __syncthreads();
+    for (int t = threadIdx.x; t < 2 * words; t += blockDim.x) used_bits[t] = 0u;
+    if (threadIdx.x == 0) {
+        s_count = 0;
+        s_done = 0;
+    }
+    const int limit = min(nA, nB);
+    double* conn = lb.conn + (size_t)k * lb.conn_capacity * 5;
+    for (int base = 0; base < n; base += CH) {
+        __syncthreads();
+        if (s_done) break;
+        const int m = min(CH, n - base);
+        for (int t = threadIdx.x; t < m; t += blockDim.x) {
+            const int c = ord[base + t];
+            s_c[t] = c;
+            s_i[t] = ij[2 * c];
+            s_j[t] = ij[2 * c + 1];
         }
-        if (c < n) ord[rank] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int count = s_count;
+            for (int r = 0; r < m && count < limit; ++r) {
+                const int i = s_i[r], j = s_j[r];
+                if (((usedA[i >> 5] >> (i & 31)) & 1u) || ((usedB[j >> 5] >> (j & 31)) & 1u)) continue;
+                usedA[i >> 5] |= 1u << (i & 31);
+                usedB[j >> 5] |= 1u << (j & 31);
+                if (count < lb.conn_capacity) {
+                    double* row = conn + (size_t)count * 5;
+                    row[0] = (double)(a0 + i);      // candidate id of A (ids are global sorted positions)
+                    row[1] = (double)(b0 + j);
+                    row[2] = sc[s_c[r]];
+                    row[3] = (double)i;
+                    row[4] = (double)j;
+                } else {
+                    atomicOr(lb.status, ST_CONN_OVERFLOW);
+                }
+                ++count;
+            }
+            s_count = count;
+            if (count >= limit) s_done = 1;
+        }
     }
     __syncthreads();
-
-    // greedy walk (src/body.py:143-150) -- inherently sequential; one thread, inputs are L1/L2 resident
-    if (threadIdx.x == 0) {
-        const int limit = min(nA, nB);
-        int count = 0;
-        double* conn = lb.conn + (size_t)k * lb.conn_capacity * 5;
-        for (int r = 0; r < n && count < limit; ++r) {
-            const int c = ord[r];
-            const int i = ij[2 * c], j = ij[2 * c + 1];
-            if (usedA[i] || usedB[j]) continue;
-            usedA[i] = 1;
-            usedB[j] = 1;
-            if (count < lb.conn_capacity) {
-                double* row = conn + (size_t)count * 5;
-                row[0] = (double)(a0 + i);      // candidate id of A (ids are global sorted positions)
-                row[1] = (double)(b0 + j);
-                row[2] = sc[c];
-                row[3] = (double)i;
-                row[4] = (double)j;
-            } else {
-                atomicOr(lb.status, ST_CONN_OVERFLOW);
-            }
-            ++count;
-        }
-        lb.conn_count[k] = min(count, lb.conn_capacity);
-    }
+    if (threadIdx.x == 0) lb.conn_count[k] = min(s_count, lb.conn_capacity);
 }
 
 // ---- subset assembly: one warp, rows in dynamic shared memory -----------------------------------------
 __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restrict__ frames) {
-    extern __shared__ double rows_shared[];          // [min(subset_capacity, kSubsetRowsShared)][20]
+    // work rows are 21 doubles apart: a lane-per-row read of one column then touches 32 different shared-memory banks
+    // (with the natural stride of 20 doubles it was an 8-way conflict on every probe of the row search)
+    constexpr int RS = kSubsetRowStride;
+    extern __shared__ double rows_shared[];          // [min(subset_capacity, kSubsetRowsShared)][RS]
     const FramePost& fr = frames[blockIdx.x];
     const double* __restrict__ cand = fr.pb.candidates;
     const LimbBuffers& lb = fr.lb;
@@ -223,16 +260,25 @@ __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restric
             const double scoreA = sconn[c][3], scoreB = sconn[c][4];
             // rows j with subset[j][indexA] == partAs[i] or subset[j][indexB] == partBs[i]
             int found = 0, j1 = -1, j2 = -1;
-            for (int base = 0; base < nrows; base += 32) {
-                const int j = base + lane;
-                const bool m = j < nrows && (rows[j * 20 + ia] == idA || rows[j * 20 + ib] == idB);
-                unsigned mask = __ballot_sync(0xffffffffu, m);
-                while (mask) {
-                    const int b = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    if (found == 0) j1 = base + b;
-                    else if (found == 1) j2 = base + b;
-                    ++found;
+            // four 32-row probes per step: their shared-memory loads are independent, so their latencies overlap (one
+            // warp walks the connections sequentially and this search is its critical path)
+            for (int base = 0; base < nrows; base += 128) {
+                bool m[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = base + u * 32 + lane;
+                    m[u] = j < nrows && (rows[j * RS + ia] == idA || rows[j * RS + ib] == idB);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    unsigned mask = __ballot_sync(0xffffffffu, m[u]);
+                    while (mask) {
+                        const int b = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if (found == 0) j1 = base + u * 32 + b;
+                        else if (found == 1) j2 = base + u * 32 + b;
+                        ++found;
+                    }
                 }
             }
             if (found > 2) {                         // reference: IndexError at src/body.py:173
@@ -242,34 +288,34 @@ __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restric
             }
             if (found == 2) {
                 // disjoint?  (membership == 2 nowhere over the 18 part slots)
-                const bool both = lane < 18 && rows[j1 * 20 + lane] >= 0.0 && rows[j2 * 20 + lane] >= 0.0;
+                const bool both = lane < 18 && rows[j1 * RS + lane] >= 0.0 && rows[j2 * RS + lane] >= 0.0;
                 const bool overlap = __ballot_sync(0xffffffffu, both) != 0;
                 if (!overlap) {
-                    if (lane < 18) rows[j1 * 20 + lane] = rows[j1 * 20 + lane] + (rows[j2 * 20 + lane] + 1.0);
-                    if (lane == 18) rows[j1 * 20 + 18] = (rows[j1 * 20 + 18] + rows[j2 * 20 + 18]) + limb_score;
-                    if (lane == 19) rows[j1 * 20 + 19] = rows[j1 * 20 + 19] + rows[j2 * 20 + 19];
+                    if (lane < 18) rows[j1 * RS + lane] = rows[j1 * RS + lane] + (rows[j2 * RS + lane] + 1.0);
+                    if (lane == 18) rows[j1 * RS + 18] = (rows[j1 * RS + 18] + rows[j2 * RS + 18]) + limb_score;
+                    if (lane == 19) rows[j1 * RS + 19] = rows[j1 * RS + 19] + rows[j2 * RS + 19];
                     __syncwarp();
                     // np.delete(subset, j2, 0): shift the tail up by one row
-                    const int first = j2 * 20, last = (nrows - 1) * 20;
+                    const int first = j2 * RS, last = (nrows - 1) * RS;
                     for (int t = first; t < last; t += 32) {
                         const int e = t + lane;
                         double v = 0.0;
-                        if (e < last) v = rows[e + 20];
+                        if (e < last) v = rows[e + RS];
                         __syncwarp();
                         if (e < last) rows[e] = v;
                         __syncwarp();
                     }
                     --nrows;
                 } else if (lane == 0) {
-                    rows[j1 * 20 + ib] = idB;
-                    rows[j1 * 20 + 19] += 1.0;
-                    rows[j1 * 20 + 18] += scoreB + limb_score;
+                    rows[j1 * RS + ib] = idB;
+                    rows[j1 * RS + 19] += 1.0;
+                    rows[j1 * RS + 18] += scoreB + limb_score;
                 }
             } else if (found == 1) {
-                if (lane == 0 && rows[j1 * 20 + ib] != idB) {
-                    rows[j1 * 20 + ib] = idB;
-                    rows[j1 * 20 + 19] += 1.0;
-                    rows[j1 * 20 + 18] += scoreB + limb_score;
+                if (lane == 0 && rows[j1 * RS + ib] != idB) {
+                    rows[j1 * RS + ib] = idB;
+                    rows[j1 * RS + 19] += 1.0;
+                    rows[j1 * RS + 18] += scoreB + limb_score;
                 }
             } else if (k < 17) {
                 if (nrows >= lb.subset_capacity) {
@@ -277,9 +323,9 @@ __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restric
                     if (lane == 0) atomicOr(lb.status, ST_SUBSET_OVERFLOW);
                     break;
                 }
-                if (lane < 18) rows[nrows * 20 + lane] = lane == ia ? idA : (lane == ib ? idB : -1.0);
-                if (lane == 18) rows[nrows * 20 + 18] = ((0.0 + scoreA) + scoreB) + limb_score;
-                if (lane == 19) rows[nrows * 20 + 19] = 2.0;
+                if (lane < 18) rows[nrows * RS + lane] = lane == ia ? idA : (lane == ib ? idB : -1.0);
+                if (lane == 18) rows[nrows * RS + 18] = ((0.0 + scoreA) + scoreB) + limb_score;
+                if (lane == 19) rows[nrows * RS + 19] = 2.0;
                 ++nrows;
             }
             __syncwarp();
@@ -293,13 +339,13 @@ __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restric
         const int j = base + lane;
         bool keep = false;
         if (j < nrows) {
-            const double parts = rows[j * 20 + 19], score = rows[j * 20 + 18];
+            const double parts = rows[j * RS + 19], score = rows[j * RS + 18];
             keep = !(parts < 4.0 || score / parts < 0.4);
         }
         const unsigned mask = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int dst = out + __popc(mask & ((1u << lane) - 1));
-            for (int q = 0; q < 20; ++q) lb.subset[(size_t)dst * 20 + q] = rows[j * 20 + q];
+            for (int q = 0; q < 20; ++q) lb.subset[(size_t)dst * 20 + q] = rows[j * RS + q];
         }
         out += __popc(mask);
     }
@@ -331,18 +377,25 @@ __global__ void __launch_bounds__(256) pack_results_kernel(const FramePost* __re
 // The per-frame counters (cand_count, status) must be zero on entry: the caller clears the plan's counter slab once
 // per batch.  subset_capacity: the largest FramePost::lb.subset_capacity of the batch.
 void paf_group_launch(const MapSource& paf, int n_frames, int H, int W, const FramePost* frames_dev, double thre2,
-                      int subset_capacity, cudaStream_t stream) {
+                      int subset_capacity, int pair_capacity, int max_part, cudaStream_t stream) {
     dim3 grid(64, kLimbs, n_frames);
     if (paf.planar != nullptr) paf_score_kernel<true><<<grid, 256, 0, stream>>>(paf, H, W, frames_dev, thre2);
     else paf_score_kernel<false><<<grid, 256, 0, stream>>>(paf, H, W, frames_dev, thre2);
     OPB_CUDA(cudaGetLastError());
-    limb_match_kernel<<<dim3(kLimbs, n_frames), 256, 0, stream>>>(frames_dev);
+    limb_sort_kernel<<<dim3(cdiv(pair_capacity, 256), kLimbs, n_frames), 256, 0, stream>>>(frames_dev);
+    OPB_CUDA(cudaGetLastError());
+    const size_t used_smem = (size_t)2 * ((max_part + 31) / 32) * sizeof(unsigned);
+    OPB_REQUIRE(used_smem <= 160 * 1024, "limb matching: too many peaks per part for the shared-memory bitmaps");
+    static bool mattr[64] = {};
+    if (first_use_on_device(mattr))
+        OPB_CUDA(cudaFuncSetAttribute(limb_match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    limb_match_kernel<<<dim3(kLimbs, n_frames), 256, used_smem, stream>>>(frames_dev);
     OPB_CUDA(cudaGetLastError());
     static bool attr[64] = {};
     if (first_use_on_device(attr)) {
-        OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubsetRowsShared * 20 * 8));
+        OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubsetRowsShared * kSubsetRowStride * 8));
     }
-    const size_t rows_smem = (size_t)std::min(subset_capacity, kSubsetRowsShared) * 20 * 8;
+    const size_t rows_smem = (size_t)std::min(subset_capacity, kSubsetRowsShared) * kSubsetRowStride * 8;
     assemble_kernel<<<n_frames, 32, rows_smem, stream>>>(frames_dev);
     OPB_CUDA(cudaGetLastError());
 }

@@ -138,3 +138,79 @@ def test_hand_peaks_giant_and_many_components():
     ref = O.hand_postprocess(hm)
     assert np.array_equal(got, ref)
     assert (ref[:, 2] > 0).sum() >= 15
+
+
+# ---- crowds beyond the default buffer sizes --------------------------------------------------------------------------
+def _candidates_from_joints(people, score=0.9):
+    """part-major candidate list [x, y, score, id] (ids cumulative, like src/body.py:88-92) from joint positions."""
+    peaks, nid = [], 0
+    for part in range(18):
+        pts = np.rint(people[:, part, :]).astype(np.float64)
+        order = np.lexsort((pts[:, 0], pts[:, 1]))                     # np.nonzero order: y, then x
+        arr = np.zeros((len(pts), 4))
+        arr[:, :2] = pts[order]
+        arr[:, 2] = score + 0.0001 * np.arange(len(pts))
+        arr[:, 3] = nid + np.arange(len(pts))
+        nid += len(pts)
+        peaks.append(arr)
+    return peaks
+
+
+def _group_on_device(paf, peaks, subset_cap, conn_cap):
+    from tests import gpu_util as G
+    cand = np.concatenate(peaks)
+    pb = [0]
+    for p in peaks:
+        pb.append(pb[-1] + len(p))
+    cand_dev = torch.from_numpy(cand).cuda()
+    return G.group_limbs(paf.transpose(2, 0, 1), cand_dev, pb, subset_cap=subset_cap, conn_cap=conn_cap)
+
+
+def test_grouping_more_persons_than_shared_memory_rows():
+    """1056 people in one frame: more person rows than the 1024 the assembly kernel keeps in shared memory -> the rows
+    spill to a global work buffer; subsets and every connection list equal the oracle (the reference has no limit)."""
+    _, paf, people = O.synthetic_scene(1656, 1452, (44, 24), seed=3, jitter=0.3)
+    peaks = _candidates_from_joints(people)
+    conns_ref, special = O.match_limbs(peaks, paf, 1656)
+    _, subset_ref = O.assemble(peaks, conns_ref, special)
+    subset, conns, cc = _group_on_device(paf, peaks, subset_cap=4096, conn_cap=2048)
+    assert len(subset_ref) > 1024
+    for k in range(19):
+        assert cc[k] == len(conns_ref[k]) and np.array_equal(conns[k, :cc[k]], conns_ref[k])
+    assert subset.shape == subset_ref.shape and np.array_equal(subset, subset_ref)
+
+
+def test_grouping_survivor_lists_grow_and_sort_across_the_gpu():
+    """A limb field that accepts almost every pair pointing its way: tens of thousands of scored survivors per limb
+    (> the 16384 the lists start with) -> the lists grow, the segmented sort ranks them on many CTAs, the greedy walk
+    keeps min(nA, nB) of them; equal to the oracle's stable sort + walk."""
+    H, W, n = 400, 600, 220
+    rng = np.random.default_rng(17)
+    people = np.zeros((n, 18, 2))
+    people[:, :, 0] = rng.integers(5, W - 5, (n, 18))
+    people[:, :, 1] = rng.integers(5, H - 5, (n, 18))
+    # distinct positions per part (peaks of one map are distinct pixels)
+    for part in range(18):
+        flat = rng.choice((H - 10) * (W - 10), n, replace=False)
+        people[:, part, 0] = 5 + flat % (W - 10)
+        people[:, part, 1] = 5 + flat // (W - 10)
+    peaks = _candidates_from_joints(people)
+    paf = np.zeros((H, W, 38))
+    paf[:, :, 0::2] = 1.0                                              # every limb's field points along +x
+    conns_ref, special = O.match_limbs(peaks, paf, H)
+    survivors = [len(O.score_pairs(paf, peaks[a - 1], peaks[b - 1], k, H)) for k, (a, b) in enumerate(O.LIMB_SEQ[:2])]
+    assert max(survivors) > 16384, survivors
+    try:
+        _, subset_ref = O.assemble(peaks, conns_ref, special)
+        raised = False
+    except IndexError:
+        raised = True
+    from pytorch_openpose_b200 import _lib
+    if raised:
+        with pytest.raises(IndexError):
+            _group_on_device(paf, peaks, subset_cap=4096, conn_cap=512)
+    else:
+        subset, conns, cc = _group_on_device(paf, peaks, subset_cap=4096, conn_cap=512)
+        for k in range(19):
+            assert cc[k] == len(conns_ref[k]) and np.array_equal(conns[k, :cc[k]], conns_ref[k])
+        assert np.array_equal(subset, subset_ref)

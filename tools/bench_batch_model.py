@@ -19,10 +19,11 @@ rng = np.random.default_rng(0)
 res = {}
 
 
-def run(est, batches, reps):
+def run(est, batches, reps, submit=None):
+    submit = submit or est.submit
     ss = [est._session, est.net.session()]
     for s, b in zip(ss, batches):                  # warm-up: plans
-        est.submit(b, s)
+        submit(b, s)
     for s in ss:
         est.collect(s)
     torch.cuda.synchronize()
@@ -32,7 +33,7 @@ def run(est, batches, reps):
         s = ss[i % 2]
         if len(pending) == 2:
             est.collect(pending.pop(0))
-        est.submit(batches[i % len(batches)], s)
+        submit(batches[i % len(batches)], s)
         pending.append(s)
     for s in pending:
         est.collect(s)
@@ -49,6 +50,12 @@ dev = [f.cuda() for f in frames]
 dt = run(body, dev, 12)
 res["batch_body_720p_b16"]["frames_per_s_device_resident_input"] = B / dt
 del dev
+# decoded uint8 frames as they come out of cv2 (what the extraction job feeds): 4x fewer bytes over PCIe than float
+# frames (16 x 11 MB instead of 16 x 11 MB x 4 = 177 MB per batch, which is what bounds the float-input figure above)
+u8 = [torch.from_numpy(rng.integers(0, 256, (B, 720, 1280, 3), dtype=np.uint8)).pin_memory() for _ in range(2)]
+dt = run(body, [u.numpy() for u in u8], 12, submit=lambda b, s: body.submit_frames(b, s, where=2))
+res["batch_body_720p_b16"]["frames_per_s_uint8_frames_from_pinned_host"] = B / dt
+del u8
 t0 = time.perf_counter()
 O.batch_body_call(frames[0][:2].numpy(), O.make_weights("body", 0))
 res["batch_body_720p_b16"]["cpu_port_frames_per_s"] = 2 / (time.perf_counter() - t0)
