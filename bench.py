@@ -167,6 +167,7 @@ def extra_hand_c3(local, barrier, max_over_ranks, world):
 
 
 def extra_bodyhand_c4(local, rank, barrier, max_over_ranks, world, streams=2, B=8, F=32, steps=4):
+    streams = int(os.environ.get("OPB_C4_STREAMS", streams))
     """config 4: 720p stream, body (4 scales) + two hands (4 scales) per frame through motion.PoseEstimator: the hand
     crops are cut (the left one mirrored) from the frame already on the device, all 2 * B crops of a batch run as one
     ragged hand batch, PoseMat (60, 3) per frame is the only result read back.  Random-init weights find no person, so
@@ -394,7 +395,7 @@ def run_ours(args):
 
     # ---- BASELINE.json's second metric: PAF-grouping ms/frame on the crowded synthetic scene (50 people) ----
     grouping = None
-    if rank == 0:
+    if rank == 0 and not args.no_grouping:
         import ctypes
         from oracle import openpose_oracle as O        # checker / CPU leg only: the synthetic 50-person scene and its CPU timing
         heat50, paf50, _ = O.synthetic_scene(H, W, (10, 5), seed=0)
@@ -484,6 +485,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="frames per batched submit (one launch per CNN layer per batch)")
     ap.add_argument("--streams", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-grouping", action="store_true", help="skip the PAF-grouping leg (50-person scene)")
     ap.add_argument("--no-extras", action="store_true", help="skip the config-3 / config-4 / decode-inclusive legs")
     ap.add_argument("--layers", default=None, help="write the per-launch profile of one frame to this CSV")
     args = ap.parse_args()

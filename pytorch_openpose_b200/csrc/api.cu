@@ -239,8 +239,13 @@ struct FramePlan {
     cudaGraphExec_t graph = nullptr;
     uint64_t graph_gen = 0;
     int uses = 0;
+    // the same for the body + hands sequence of opb_pose_submit_batch (a different launch list over the same buffers)
+    cudaGraphExec_t pose_graph = nullptr;
+    uint64_t pose_gen = 0;
+    int pose_uses = 0;
     ~FramePlan() {
         if (graph) cudaGraphExecDestroy(graph);
+        if (pose_graph) cudaGraphExecDestroy(pose_graph);
     }
     std::vector<ScaleDims> dims;
     std::vector<U8Taps> u8taps;
@@ -566,36 +571,45 @@ static FramePlan* get_plan(opb_session* s, int n, int H, int W, const double* sc
 // Runs `enqueue` (kernel launches, memsets and result copies on the session's stream) either directly or, once the plan
 // has been used a few times, as one CUDA graph launch: a frame is ~70 small dependent launches, and for the small
 // default configuration (640x480, one scale) the launch gaps, not the kernels, are most of the latency.
+struct GraphSlot {
+    cudaGraphExec_t& graph;
+    uint64_t& gen;
+    int& uses;
+};
 template <typename F>
-static void run_or_replay(opb_session* s, FramePlan* fp, F&& enqueue) {
+static void run_or_replay_slot(opb_session* s, GraphSlot g, uint64_t want_gen, F&& enqueue) {
     static const bool no_graph = getenv("OPB_NO_GRAPH") != nullptr;
     cudaStream_t st = s->stream;
-    ++fp->uses;
-    if (no_graph || s->prof.on || fp->uses < 3) {       // first uses run eagerly (lazy module loading, attributes)
+    ++g.uses;
+    if (no_graph || s->prof.on || g.uses < 3) {         // first uses run eagerly (lazy module loading, attributes)
         enqueue();
         return;
     }
-    if (!fp->graph || fp->graph_gen != s->buffer_gen) {
-        if (fp->graph) {
-            cudaGraphExecDestroy(fp->graph);
-            fp->graph = nullptr;
+    if (!g.graph || g.gen != want_gen) {
+        if (g.graph) {
+            cudaGraphExecDestroy(g.graph);
+            g.graph = nullptr;
         }
-        cudaGraph_t g = nullptr;
+        cudaGraph_t cg = nullptr;
         OPB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
         try {
             enqueue();
         } catch (...) {
-            cudaStreamEndCapture(st, &g);
-            if (g) cudaGraphDestroy(g);
+            cudaStreamEndCapture(st, &cg);
+            if (cg) cudaGraphDestroy(cg);
             throw;
         }
-        OPB_CUDA(cudaStreamEndCapture(st, &g));
-        const cudaError_t e = cudaGraphInstantiate(&fp->graph, g, 0);
-        cudaGraphDestroy(g);
+        OPB_CUDA(cudaStreamEndCapture(st, &cg));
+        const cudaError_t e = cudaGraphInstantiate(&g.graph, cg, 0);
+        cudaGraphDestroy(cg);
         OPB_CUDA(e);
-        fp->graph_gen = s->buffer_gen;
+        g.gen = want_gen;
     }
-    OPB_CUDA(cudaGraphLaunch(fp->graph, st));
+    OPB_CUDA(cudaGraphLaunch(g.graph, st));
+}
+template <typename F>
+static void run_or_replay(opb_session* s, FramePlan* fp, F&& enqueue) {
+    run_or_replay_slot(s, GraphSlot{fp->graph, fp->graph_gen, fp->uses}, s->buffer_gen, enqueue);
 }
 
 static void upload_image(opb_session* s, FramePlan* fp, const uint8_t* img, int where, size_t bytes) {
@@ -997,8 +1011,6 @@ static void pose_submit(opb_session* bs, opb_session* hs, const uint8_t* imgs, i
     bs->pose_hand = hs;
     cudaStream_t st = bs->stream;
     upload_image(bs, fp, imgs, where, (size_t)n * H * W * 3);
-    run_front(bs, fp, n, H, W);
-    body_post_enqueue(bs, fp, n, H, W);
     // hand part on the same stream, with the hand session's CNN plan and work buffers (sized for the largest crop)
     OPB_CUDA(cudaStreamSynchronize(hs->stream));               // nothing of the hand session's own stream may still use them
     FramePlan* hp = get_plan(hs, slots, tw, tw, hscales, nhs);
@@ -1008,23 +1020,32 @@ static void pose_submit(opb_session* bs, opb_session* hs, const uint8_t* imgs, i
     if (fixed_boxes) {
         OPB_CUDA(cudaStreamSynchronize(st));                   // the pinned copy of the previous batch's boxes is free
         memcpy(bs->pose->fixed_host, fixed_boxes, (size_t)n * 6 * sizeof(int));
-        OPB_CUDA(cudaMemcpyAsync(bs->pose->fixed, bs->pose->fixed_host, (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice, st));
         fixed_dev = bs->pose->fixed;
     }
-    pose_select_launch(fp->post_dev, n, H, W, fixed_dev, bs->pose->pose, bs->pose->boxes, bs->pose->dims, st);
     const opb_session::Ragged& rg = *hs->ragged;
-    const float* src[kMaxScales];
-    int ho[kMaxScales], wo[kMaxScales];
-    for (int s = 0; s < nhs; ++s) {
-        preprocess_ragged_launch(fp->d_img, H, W, bs->pose->boxes, slots, hp->net->in_u8[s], rg.net_side[s], s, rg.tabs, st);
-        src[s] = hp->net->out_heat[s];
-        ho[s] = wo[s] = rg.net_side[s] / 8;
-    }
-    hp->net->run(st, nullptr);
-    upsample_ragged_launch(src, ho, wo, nhs, 24, 22, bs->pose->boxes, slots, rg.tabs, tw, hp->up_scratch, hp->heat_avg, st);
-    hand_peaks_ragged_launch(hp->heat_avg, slots, 22, bs->pose->dims, tw, 0.03, hp->hb, st);      // thre, src/hand.py:31
-    pose_finish_launch(bs->pose->boxes, hp->hb.peaks, n, bs->pose->pose, st);
-    OPB_CUDA(cudaMemcpyAsync(bs->pose->host, bs->pose->pose, (size_t)n * 180 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    // everything between the frame upload and the PoseMat copy is one launch sequence on one stream: replayed as a CUDA
+    // graph from the third use on (re-captured when a buffer of either session, the hand plan or the box source changed)
+    const uint64_t gen = bs->buffer_gen * 1000003ull + hs->buffer_gen * 7919ull + (uint64_t)(uintptr_t)hp +
+                         (uint64_t)(uintptr_t)rg.tabs.slab + (fixed_dev ? 1 : 0);
+    run_or_replay_slot(bs, GraphSlot{fp->pose_graph, fp->pose_gen, fp->pose_uses}, gen, [&] {
+        run_front(bs, fp, n, H, W);
+        body_post_enqueue(bs, fp, n, H, W);
+        if (fixed_dev)
+            OPB_CUDA(cudaMemcpyAsync(bs->pose->fixed, bs->pose->fixed_host, (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+        pose_select_launch(fp->post_dev, n, H, W, fixed_dev, bs->pose->pose, bs->pose->boxes, bs->pose->dims, st);
+        const float* src[kMaxScales];
+        int ho[kMaxScales], wo[kMaxScales];
+        for (int s = 0; s < nhs; ++s) {
+            preprocess_ragged_launch(fp->d_img, H, W, bs->pose->boxes, slots, hp->net->in_u8[s], rg.net_side[s], s, rg.tabs, st);
+            src[s] = hp->net->out_heat[s];
+            ho[s] = wo[s] = rg.net_side[s] / 8;
+        }
+        hp->net->run(st, nullptr);
+        upsample_ragged_launch(src, ho, wo, nhs, 24, 22, bs->pose->boxes, slots, rg.tabs, tw, hp->up_scratch, hp->heat_avg, st);
+        hand_peaks_ragged_launch(hp->heat_avg, slots, 22, bs->pose->dims, tw, 0.03, hp->hb, st);      // thre, src/hand.py:31
+        pose_finish_launch(bs->pose->boxes, hp->hb.peaks, n, bs->pose->pose, st);
+        OPB_CUDA(cudaMemcpyAsync(bs->pose->host, bs->pose->pose, (size_t)n * 180 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    });
     OPB_CUDA(cudaEventRecord(bs->done, st));
     bs->net->ctx->launches += fp->launches_per_frame + nhs + hp->net->kernel_launches + (nhs + 1) + 6 + 2;
 }
@@ -1515,10 +1536,10 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int H, int W, const 
         int status[4], count = 0;
         std::unique_ptr<StagePost> spp;
         // the survivor lists grow on demand, like in the frame path (the reference has no limit)
-        for (int pair_cap = kPairCapacity;; pair_cap *= 4) {
+        int pair_cap = kPairCapacity, rows_cap = std::max(subset_capacity, 1);
+        for (;;) {
             spp = std::make_unique<StagePost>();
-            spp->create(std::max(total, 1), pair_cap, conn_cap, std::max(subset_capacity, 1), const_cast<double*>(dev_candidates),
-                        ctx->stream);
+            spp->create(std::max(total, 1), pair_cap, conn_cap, rows_cap, const_cast<double*>(dev_candidates), ctx->stream);
             OPB_CUDA(cudaMemcpyAsync(spp->host.pb.part_begin, host_part_begin19, 19 * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
             paf_group_launch(src, 1, H, W, spp->dev, thre2, spp->host.lb.subset_capacity, spp->host.lb.pair_capacity,
                              spp->host.lb.max_part, ctx->stream);
@@ -1526,7 +1547,11 @@ int opb_group_limbs(opb_context* ctx, const float* dev_paf, int H, int W, const 
             OPB_CUDA(cudaMemcpyAsync(status, spp->host.lb.status, sizeof(status), cudaMemcpyDeviceToHost, ctx->stream));
             OPB_CUDA(cudaMemcpyAsync(&count, spp->host.lb.subset_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
             OPB_CUDA(cudaStreamSynchronize(ctx->stream));
-            if (!(status[0] & kStPairOverflow) || pair_cap >= (1 << 20)) break;
+            const bool more_pairs = (status[0] & kStPairOverflow) && pair_cap < (1 << 20);
+            const bool more_rows = (status[0] & kStSubsetOverflow) && rows_cap < (1 << 16);
+            if (!more_pairs && !more_rows) break;
+            if (more_pairs) pair_cap *= 4;
+            if (more_rows) rows_cap *= 4;      // work rows before pruning; beyond 1024 they live in global memory
         }
         StagePost& sp = *spp;
         if (status[0] & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))

@@ -149,72 +149,77 @@ __global__ void hand_runs_kernel(int* __restrict__ labels, int h, int w, const i
 }
 
 // (2) unite every run with the runs of the row above that touch it (columns xs-1 .. xe+1)
+constexpr int kRowsPerBlock = 16;     // rows a block of the per-pixel passes walks (ragged batches size their grids for the largest crop)
 __global__ void hand_merge_kernel(int* __restrict__ labels, int h, int w, const int* __restrict__ dims, size_t ps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
     OPB_HAND_GEOM(blockIdx.z / 21)
-    if (x >= w || y == 0 || y >= h) return;
+    if (x >= w) return;
     int* L = labels + (size_t)blockIdx.z * ps;
-    const int i = y * w + x;
-    const int mine = L[i];
-    if (mine < 0) return;
-    const int* up = L + i - w;
-    const bool u0 = up[0] >= 0;
-    // an upper run that STARTS at x+1 touches this run
-    if (x + 1 < w && up[1] >= 0 && !u0) uf_union(L, mine, up[1]);
-    // at the head of this run (decided by geometry: the head's own entry may already have been hooked by another
-    // thread): the upper run covering x-1 or x
-    if (x == 0 || L[i - 1] < 0) {
-        if (x > 0 && up[-1] >= 0) uf_union(L, mine, up[-1]);
-        else if (u0) uf_union(L, mine, up[0]);
+    for (int y = max(1, (int)blockIdx.y * kRowsPerBlock); y < min(h, ((int)blockIdx.y + 1) * kRowsPerBlock); ++y) {
+        const int i = y * w + x;
+        const int mine = L[i];
+        if (mine < 0) continue;
+        const int* up = L + i - w;
+        const bool u0 = up[0] >= 0;
+        // an upper run that STARTS at x+1 touches this run
+        if (x + 1 < w && up[1] >= 0 && !u0) uf_union(L, mine, up[1]);
+        // at the head of this run (decided by geometry: the head's own entry may already have been hooked by another
+        // thread): the upper run covering x-1 or x
+        if (x == 0 || L[i - 1] < 0) {
+            if (x > 0 && up[-1] >= 0) uf_union(L, mine, up[-1]);
+            else if (u0) uf_union(L, mine, up[0]);
+        }
     }
 }
 
 // (3) compress run heads to their roots
 __global__ void hand_compress_kernel(int* __restrict__ labels, int h, int w, const int* __restrict__ dims, size_t ps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
     OPB_HAND_GEOM(blockIdx.z / 21)
-    if (x >= w || y >= h) return;
+    if (x >= w) return;
     int* L = labels + (size_t)blockIdx.z * ps;
-    const int i = y * w + x;
-    if (L[i] < 0) return;
-    const bool head = x == 0 || L[i - 1] < 0;
-    if (!head) return;
-    const int root = uf_find(L, i);
-    if (root != i) L[i] = root;                        // only ever lowers an entry towards its root
+    for (int y = blockIdx.y * kRowsPerBlock; y < min(h, ((int)blockIdx.y + 1) * kRowsPerBlock); ++y) {
+        const int i = y * w + x;
+        if (L[i] < 0) continue;
+        const bool head = x == 0 || L[i - 1] < 0;
+        if (!head) continue;
+        const int root = uf_find(L, i);
+        if (root != i) L[i] = root;                        // only ever lowers an entry towards its root
+    }
 }
 
 // (4) resolve every pixel and accumulate the raw-map sum of its component
 __global__ void hand_flatten_kernel(const float* __restrict__ heat, int chan_stride_maps, int* __restrict__ labels,
                                     double* __restrict__ sums, int h, int w, const int* __restrict__ dims, size_t ps) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
     const int m = blockIdx.z;
     const int crop = m / 21, part = m - crop * 21;
     OPB_HAND_GEOM(crop)
     int* L = labels + (size_t)m * ps;
-    const int i = y * w + x;
-    int root = -1;
-    double v = 0.0;
-    if (x < w && y < h && L[i] >= 0) {
-        root = __ldcg(L + __ldcg(L + i));              // pixel -> run head -> root
-        // a run head may itself still point one hop short if it was hooked after its own compression pass started
-        root = uf_find(L, root);
-        L[i] = root;
-        v = (double)heat[((size_t)crop * chan_stride_maps + part) * ps + i];
-    }
-    // warp-aggregated atomics: lanes of a warp almost always share one root
-    const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
-    if (root < 0) return;
-    const unsigned same = __match_any_sync(active, root);
-    if (active == 0xffffffffu && same == active) {
-        double tot = v;
+    if ((int)(blockIdx.x * blockDim.x) >= w) return;
+    for (int y = blockIdx.y * kRowsPerBlock; y < min(h, ((int)blockIdx.y + 1) * kRowsPerBlock); ++y) {
+        const int i = y * w + x;
+        int root = -1;
+        double v = 0.0;
+        if (x < w && L[i] >= 0) {
+            root = __ldcg(L + __ldcg(L + i));              // pixel -> run head -> root
+            // a run head may itself still point one hop short if it was hooked after its own compression pass started
+            root = uf_find(L, root);
+            L[i] = root;
+            v = (double)heat[((size_t)crop * chan_stride_maps + part) * ps + i];
+        }
+        // warp-aggregated atomics: lanes of a warp almost always share one root
+        const unsigned active = __ballot_sync(0xffffffffu, root >= 0);
+        if (root < 0) continue;
+        const unsigned same = __match_any_sync(active, root);
+        if (active == 0xffffffffu && same == active) {
+            double tot = v;
 #pragma unroll
-        for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
-        if ((threadIdx.x & 31) == 0) atomicAdd(&sums[(size_t)m * ps + root], tot);
-    } else {
-        atomicAdd(&sums[(size_t)m * ps + root], v);
+            for (int o = 16; o; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&sums[(size_t)m * ps + root], tot);
+        } else {
+            atomicAdd(&sums[(size_t)m * ps + root], v);
+        }
     }
 }
 
@@ -334,7 +339,7 @@ void hand_peaks_ragged_launch(const float* heat_planar, int n_crops, int chan_st
 // labels hold the mask (own raster index or -1): components, per-component sums, selection (src/hand.py:68-74)
 static void hand_components_launch(const float* heat_planar, int maps, int chan_stride_maps, int h, int w, HandBuffers hb,
                                    const int* dims, size_t ps, cudaStream_t stream) {
-    dim3 g2(cdiv(w, 128), h, maps);
+    dim3 g2(cdiv(w, 128), cdiv(h, kRowsPerBlock), maps);
     dim3 g0(cdiv(h, 4), maps);
     hand_runs_kernel<<<g0, 128, 0, stream>>>(hb.labels, h, w, dims, ps);
     OPB_CUDA(cudaGetLastError());

@@ -344,28 +344,30 @@ struct UpYRagged {
     int n_scales;
 };
 // y pass: the chain of upsample_y_kernel with per-slot tables; out[slot][c][y][x], plane pitch w_slot, plane stride ps
+constexpr int kRaggedRows = 16;       // output rows per block (the grid is sized for the largest possible crop)
 __global__ void upsample_y_ragged_kernel(const __grid_constant__ UpYRagged p, int C, const HandBox* __restrict__ boxes,
                                          const RaggedTables tabs, int wmax, size_t ps, float* __restrict__ out) {
     const int x = blockIdx.x * blockDim.x + threadIdx.x;
-    const int y = blockIdx.y;
     const int slot = blockIdx.z / C, c = blockIdx.z - slot * C;
     const HandBox b = boxes[slot];
-    if (!b.valid || x >= b.w || y >= b.w) return;
+    if (!b.valid || x >= b.w) return;
     const int w = b.w;
-    float acc = 0.f;
-    for (int s = 0; s < p.n_scales; ++s) {
-        const int* yfirst = (const int*)ragged_table(tabs, w, s, 2);
-        const float* yw = (const float*)ragged_table(tabs, w, s, 4);
-        const int f = yfirst[y];
-        const int ho = p.ho[s];
-        const float* t = p.tmp[s] + (size_t)slot * C * ho * wmax + (size_t)c * ho * w + x;
+    for (int y = blockIdx.y * kRaggedRows; y < min(w, ((int)blockIdx.y + 1) * kRaggedRows); ++y) {
+        float acc = 0.f;
+        for (int s = 0; s < p.n_scales; ++s) {
+            const int* yfirst = (const int*)ragged_table(tabs, w, s, 2);
+            const float* yw = (const float*)ragged_table(tabs, w, s, 4);
+            const int f = yfirst[y];
+            const int ho = p.ho[s];
+            const float* t = p.tmp[s] + (size_t)slot * C * ho * wmax + (size_t)c * ho * w + x;
 #pragma unroll
-        for (int k = 0; k < kUpTaps; ++k) {
-            const int r = min(f + k, ho - 1);
-            acc = fmaf(yw[y * kUpTaps + k], t[(size_t)r * w], acc);
+            for (int k = 0; k < kUpTaps; ++k) {
+                const int r = min(f + k, ho - 1);
+                acc = fmaf(yw[y * kUpTaps + k], t[(size_t)r * w], acc);
+            }
         }
+        out[((size_t)slot * C + c) * ps + (size_t)y * w + x] = acc;
     }
-    out[((size_t)slot * C + c) * ps + (size_t)y * w + x] = acc;
 }
 
 }  // namespace
@@ -404,7 +406,7 @@ void upsample_ragged_launch(const float* const* src, const int* ho, const int* w
         p.tmp[s] = tmp;
         p.ho[s] = ho[s];
     }
-    dim3 grid(cdiv(wmax, 128), wmax, n_slots * C);
+    dim3 grid(cdiv(wmax, 128), cdiv(wmax, kRaggedRows), n_slots * C);
     upsample_y_ragged_kernel<<<grid, 128, 0, stream>>>(p, C, boxes, tabs, wmax, (size_t)wmax * wmax, out_planar);
     OPB_CUDA(cudaGetLastError());
 }

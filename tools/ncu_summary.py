@@ -14,7 +14,9 @@ WANT = ["Kernel Name", "Grid Size", "Block Size", "gpu__time_duration.sum", "dra
         "sm__cycles_elapsed.avg.per_second", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum",
         "lts__t_bytes.sum", "lts__t_sectors_srcunit_tex_op_read.sum", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed_op_tma_ld.sum"]
+        "sm__inst_executed_pipe_uniform.sum", "smsp__inst_executed_op_tma_ld.sum",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fp64.sum", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem"]
 
 
 def main(path):
