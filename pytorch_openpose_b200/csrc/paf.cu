@@ -11,8 +11,8 @@
 //                     == Python's stable sorted(..., reverse=True) over the (i, j) loop order, in one launch.
 //   limb_match_kernel one CTA per (frame, limb): the greedy walk over the sorted survivors.
 //   assemble_kernel   one warp: the reference's sequential row merge (found==1 / found==2 / new row, k < 17),
-//                     rows kept in shared memory (in a global work buffer beyond 1024 rows), row search parallel
-//                     over lanes, then pruning.
+//                     rows kept in shared memory (in a global work buffer beyond 1024 rows), matching rows found
+//                     through per-candidate owner lists, then pruning.
 // The PAF values come either from materialised planes or straight from the low-resolution net outputs
 // (composite.cuh: the same fmaf chains as the materialising kernels, so the samples are bit-identical to the planes
 // opb_body_maps returns) -- a frame needs 10 samples per candidate pair, not 38 full-resolution planes.
@@ -217,24 +217,85 @@ __global__ void __launch_bounds__(256) limb_match_kernel(const FramePost* __rest
     if (threadIdx.x == 0) lb.conn_count[k] = min(s_count, lb.conn_capacity);
 }
 
-// ---- subset assembly: one warp, rows in dynamic shared memory -----------------------------------------
+// ---- subset assembly (src/body.py:157-212): one warp ----------------------------------------------------------------
+// The reference walks the limbs and their connections in order; for each it looks for the rows that hold candidate A
+// in column a or candidate B in column b and extends / merges / creates rows.  The walk is sequential by definition,
+// so its cost is the latency of one connection.  Two things keep that short:
+//   * owner lists: for every candidate the (at most 3) rows that currently hold it, so "which rows match" is two
+//     16-byte loads instead of a scan over all rows (a candidate held by more rows falls back to the scan);
+//   * np.delete(subset, j2, 0) after a merge is a tombstone (slot 20 of the row): deleting only shifts later rows up,
+//     it never reorders them, so skipping dead rows when the result is written gives the same row order.
+// Rows live in shared memory (21 doubles apart: conflict-free column reads in the fallback scan) or, beyond 1024 rows,
+// in the frame's global work buffer; the owner lists likewise (shared up to kOwnerShared candidates).
+constexpr int kOwnerShared = 2048;
+
+__device__ __forceinline__ void owner_add(int4* own, int id, int row, bool& overflow) {
+    int4 o = own[id];
+    if (o.x < 0) o.x = row;
+    else if (o.y < 0) o.y = row;
+    else if (o.z < 0) o.z = row;
+    else {
+        o.w = 1;                      // more than three rows hold this candidate: scan for it from now on
+        overflow = true;
+    }
+    own[id] = o;
+}
+__device__ __forceinline__ void owner_remove(int4* own, int id, int row) {
+    int4 o = own[id];
+    if (o.x == row) o.x = -1;
+    else if (o.y == row) o.y = -1;
+    else if (o.z == row) o.z = -1;
+    own[id] = o;
+}
+__device__ __forceinline__ void owner_replace(int4* own, int id, int from, int to) {
+    int4 o = own[id];
+    if (o.x == from) o.x = to;
+    else if (o.y == from) o.y = to;
+    else if (o.z == from) o.z = to;
+    own[id] = o;
+}
+// smallest, second smallest and number of distinct non-negative values among six entries
+__device__ __forceinline__ void two_smallest(const int e[6], int& found, int& j1, int& j2) {
+    j1 = 0x7fffffff;
+    j2 = 0x7fffffff;
+    found = 0;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const int v = e[i];
+        if (v < 0 || v == j1 || v == j2) continue;
+        bool dup = false;
+#pragma unroll
+        for (int q = 0; q < i; ++q) dup |= e[q] == v;
+        if (dup) continue;
+        ++found;
+        if (v < j1) {
+            j2 = j1;
+            j1 = v;
+        } else if (v < j2) {
+            j2 = v;
+        }
+    }
+    if (found < 2) j2 = -1;
+    if (found < 1) j1 = -1;
+}
+
 __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restrict__ frames) {
-    // work rows are 21 doubles apart: a lane-per-row read of one column then touches 32 different shared-memory banks
-    // (with the natural stride of 20 doubles it was an 8-way conflict on every probe of the row search)
     constexpr int RS = kSubsetRowStride;
-    extern __shared__ double rows_shared[];          // [min(subset_capacity, kSubsetRowsShared)][RS]
+    extern __shared__ double rows_shared[];          // [min(subset_capacity, kSubsetRowsShared)][RS], then the owner lists
     const FramePost& fr = frames[blockIdx.x];
     const double* __restrict__ cand = fr.pb.candidates;
     const LimbBuffers& lb = fr.lb;
-    // work rows: shared memory, or the frame's global work buffer once a frame has needed more rows than fit
     double* rows = lb.rows_global ? lb.rows_global : rows_shared;
+    const int n_cand = min(fr.pb.part_begin[18], fr.pb.capacity);
+    const size_t rows_bytes = ((size_t)(lb.rows_global ? 0 : min(lb.subset_capacity, kSubsetRowsShared)) * RS * 8 + 15) & ~(size_t)15;
+    int4* own = n_cand <= kOwnerShared ? (int4*)((uint8_t*)rows_shared + rows_bytes) : lb.owner_global;
     const int lane = threadIdx.x;
     int nrows = 0;
-    bool fail = false;
+    bool fail = false, own_overflow = false;
+    for (int t = lane; t < n_cand; t += 32) own[t] = make_int4(-1, -1, -1, 0);
 
     // connections are staged through shared memory in chunks (coalesced loads, candidate scores gathered in
-    // parallel): the sequential merge below then never waits on global memory (it used to pay two dependent
-    // global round trips per connection: 730 us for 950 connections)
+    // parallel): the sequential merge below then never waits on global memory
     constexpr int CH = 256;
     __shared__ double sconn[CH][5];                  // idA, idB, limb score, score(candA), score(candB)
     for (int k = 0; k < kLimbs && !fail; ++k) {
@@ -255,90 +316,104 @@ __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restric
                 sconn[t][4] = cand[(size_t)(int)b * 4 + 2];
             }
             __syncwarp();
-        for (int c = 0; c < nch && !fail; ++c) {
-            const double idA = sconn[c][0], idB = sconn[c][1], limb_score = sconn[c][2];
-            const double scoreA = sconn[c][3], scoreB = sconn[c][4];
-            // rows j with subset[j][indexA] == partAs[i] or subset[j][indexB] == partBs[i]
-            int found = 0, j1 = -1, j2 = -1;
-            // four 32-row probes per step: their shared-memory loads are independent, so their latencies overlap (one
-            // warp walks the connections sequentially and this search is its critical path)
-            for (int base = 0; base < nrows; base += 128) {
-                bool m[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int j = base + u * 32 + lane;
-                    m[u] = j < nrows && (rows[j * RS + ia] == idA || rows[j * RS + ib] == idB);
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    unsigned mask = __ballot_sync(0xffffffffu, m[u]);
-                    while (mask) {
-                        const int b = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        if (found == 0) j1 = base + u * 32 + b;
-                        else if (found == 1) j2 = base + u * 32 + b;
-                        ++found;
+            for (int c = 0; c < nch && !fail; ++c) {
+                const double idA = sconn[c][0], idB = sconn[c][1], limb_score = sconn[c][2];
+                const double scoreA = sconn[c][3], scoreB = sconn[c][4];
+                const int a_id = (int)idA, b_id = (int)idB;
+                // rows j with subset[j][indexA] == partAs[i] or subset[j][indexB] == partBs[i] (every lane computes the
+                // same answer: the warp stays converged, nothing to exchange)
+                int found, j1, j2;
+                const int4 oa = own[a_id], ob = own[b_id];
+                if ((oa.w | ob.w) == 0) {
+                    const int e[6] = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z};
+                    two_smallest(e, found, j1, j2);
+                } else {
+                    found = 0;
+                    j1 = j2 = -1;
+                    for (int base = 0; base < nrows; base += 32) {
+                        const int j = base + lane;
+                        const bool m = j < nrows && rows[j * RS + 20] == 0.0 &&
+                                       (rows[j * RS + ia] == idA || rows[j * RS + ib] == idB);
+                        unsigned mask = __ballot_sync(0xffffffffu, m);
+                        while (mask) {
+                            const int bpos = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            if (found == 0) j1 = base + bpos;
+                            else if (found == 1) j2 = base + bpos;
+                            ++found;
+                        }
                     }
                 }
-            }
-            if (found > 2) {                         // reference: IndexError at src/body.py:173
-                fail = true;
-                if (lane == 0) atomicOr(lb.status, ST_INDEX_ERROR);
-                break;
-            }
-            if (found == 2) {
-                // disjoint?  (membership == 2 nowhere over the 18 part slots)
-                const bool both = lane < 18 && rows[j1 * RS + lane] >= 0.0 && rows[j2 * RS + lane] >= 0.0;
-                const bool overlap = __ballot_sync(0xffffffffu, both) != 0;
-                if (!overlap) {
-                    if (lane < 18) rows[j1 * RS + lane] = rows[j1 * RS + lane] + (rows[j2 * RS + lane] + 1.0);
-                    if (lane == 18) rows[j1 * RS + 18] = (rows[j1 * RS + 18] + rows[j2 * RS + 18]) + limb_score;
-                    if (lane == 19) rows[j1 * RS + 19] = rows[j1 * RS + 19] + rows[j2 * RS + 19];
-                    __syncwarp();
-                    // np.delete(subset, j2, 0): shift the tail up by one row
-                    const int first = j2 * RS, last = (nrows - 1) * RS;
-                    for (int t = first; t < last; t += 32) {
-                        const int e = t + lane;
-                        double v = 0.0;
-                        if (e < last) v = rows[e + RS];
-                        __syncwarp();
-                        if (e < last) rows[e] = v;
-                        __syncwarp();
-                    }
-                    --nrows;
-                } else if (lane == 0) {
-                    rows[j1 * RS + ib] = idB;
-                    rows[j1 * RS + 19] += 1.0;
-                    rows[j1 * RS + 18] += scoreB + limb_score;
-                }
-            } else if (found == 1) {
-                if (lane == 0 && rows[j1 * RS + ib] != idB) {
-                    rows[j1 * RS + ib] = idB;
-                    rows[j1 * RS + 19] += 1.0;
-                    rows[j1 * RS + 18] += scoreB + limb_score;
-                }
-            } else if (k < 17) {
-                if (nrows >= lb.subset_capacity) {
+                if (found > 2) {                         // reference: IndexError at src/body.py:173
                     fail = true;
-                    if (lane == 0) atomicOr(lb.status, ST_SUBSET_OVERFLOW);
+                    if (lane == 0) atomicOr(lb.status, ST_INDEX_ERROR);
                     break;
                 }
-                if (lane < 18) rows[nrows * RS + lane] = lane == ia ? idA : (lane == ib ? idB : -1.0);
-                if (lane == 18) rows[nrows * RS + 18] = ((0.0 + scoreA) + scoreB) + limb_score;
-                if (lane == 19) rows[nrows * RS + 19] = 2.0;
-                ++nrows;
+                bool extend = found == 1;                // "row j1 gets candidate B" (also the overlapping found == 2 case)
+                if (found == 2) {
+                    // disjoint?  (membership == 2 nowhere over the 18 part slots)
+                    const bool both = lane < 18 && rows[j1 * RS + lane] >= 0.0 && rows[j2 * RS + lane] >= 0.0;
+                    const bool overlap = __ballot_sync(0xffffffffu, both) != 0;
+                    if (!overlap) {
+                        // subset[j1][:-2] += subset[j2][:-2] + 1 ; tails summed ; + limb score ; row j2 deleted
+                        double moved = -1.0;
+                        if (lane < 18) {
+                            moved = rows[j2 * RS + lane];
+                            rows[j1 * RS + lane] = rows[j1 * RS + lane] + (moved + 1.0);
+                        }
+                        if (lane == 18) rows[j1 * RS + 18] = (rows[j1 * RS + 18] + rows[j2 * RS + 18]) + limb_score;
+                        if (lane == 19) rows[j1 * RS + 19] = rows[j1 * RS + 19] + rows[j2 * RS + 19];
+                        if (lane == 20) rows[j2 * RS + 20] = 1.0;                     // tombstone
+                        __syncwarp();
+                        // candidates of the deleted row now belong to row j1 (one lane at a time: two parts of the row
+                        // never share a candidate, but the owner entries are read-modify-write)
+                        if (lane < 18 && moved >= 0.0) owner_replace(own, (int)moved, j2, j1);
+                        __syncwarp();
+                    } else {
+                        extend = true;
+                    }
+                } else if (found == 0 && k < 17) {
+                    if (nrows >= lb.subset_capacity) {
+                        fail = true;
+                        if (lane == 0) atomicOr(lb.status, ST_SUBSET_OVERFLOW);
+                        break;
+                    }
+                    if (lane < 18) rows[nrows * RS + lane] = lane == ia ? idA : (lane == ib ? idB : -1.0);
+                    if (lane == 18) rows[nrows * RS + 18] = ((0.0 + scoreA) + scoreB) + limb_score;
+                    if (lane == 19) rows[nrows * RS + 19] = 2.0;
+                    if (lane == 20) rows[nrows * RS + 20] = 0.0;
+                    if (lane == 0) {
+                        owner_add(own, a_id, nrows, own_overflow);
+                        if (b_id != a_id) owner_add(own, b_id, nrows, own_overflow);
+                    }
+                    ++nrows;
+                }
+                if (extend) {
+                    // found == 1 (src/body.py:176-181) and the overlapping found == 2 case (:189-193)
+                    if (lane == 0) {
+                        const double old = rows[j1 * RS + ib];
+                        if (found == 2 || old != idB) {
+                            if (old != idB) {
+                                if (old >= 0.0) owner_remove(own, (int)old, j1);      // overwritten, as in the reference
+                                owner_add(own, b_id, j1, own_overflow);
+                            }
+                            rows[j1 * RS + ib] = idB;
+                            rows[j1 * RS + 19] += 1.0;
+                            rows[j1 * RS + 18] += scoreB + limb_score;
+                        }
+                    }
+                }
+                __syncwarp();
             }
-            __syncwarp();
-        }
         }
     }
     __syncwarp();
-    // prune (src/body.py:204-208) and write out in order
+    // prune (src/body.py:204-208) and write out in order, skipping deleted rows
     int out = 0;
     for (int base = 0; base < nrows; base += 32) {
         const int j = base + lane;
         bool keep = false;
-        if (j < nrows) {
+        if (j < nrows && rows[j * RS + 20] == 0.0) {
             const double parts = rows[j * RS + 19], score = rows[j * RS + 18];
             keep = !(parts < 4.0 || score / parts < 0.4);
         }
@@ -393,10 +468,12 @@ void paf_group_launch(const MapSource& paf, int n_frames, int H, int W, const Fr
     OPB_CUDA(cudaGetLastError());
     static bool attr[64] = {};
     if (first_use_on_device(attr)) {
-        OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSubsetRowsShared * kSubsetRowStride * 8));
+        OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSubsetRowsShared * kSubsetRowStride * 8 + 16 + kOwnerShared * 16));
     }
-    const size_t rows_smem = (size_t)std::min(subset_capacity, kSubsetRowsShared) * kSubsetRowStride * 8;
-    assemble_kernel<<<n_frames, 32, rows_smem, stream>>>(frames_dev);
+    // work rows (shared up to kSubsetRowsShared rows, else the frames' global buffers) + owner lists of the candidates
+    const size_t rows_smem = (size_t)std::min(subset_capacity, kSubsetRowsShared) * kSubsetRowStride * 8 + 16;
+    assemble_kernel<<<n_frames, 32, rows_smem + kOwnerShared * 16, stream>>>(frames_dev);
     OPB_CUDA(cudaGetLastError());
 }
 
