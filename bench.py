@@ -454,8 +454,9 @@ def run_ours(args):
         px_out = sum(a * b for a, b in ((23, 41), (46, 82), (69, 123), (92, 164)))
         alg_mb = {"preprocess": (H * W * 3 + px_in * 3) / 1e6,                        # uint8 frame in, uint8 padded scales out
                   "conv_first": (px_in * 3 + px_in * 64 * 2) / 1e6,                    # conv1_1: K = 27, output-write bound
-                  "upsample_avg": (px_out * 57 * 4 + H * W * 57 * 4) / 1e6,            # fp32 net maps in, fp32 full-size maps out
-                  "smooth_nms": (H * W * 18 * 4) / 1e6}
+                  # fused upsample + smoothing + NMS: the low-resolution heat maps (24-channel fp32 pixels) are read once
+                  # by the tile-bound pass and once by the peak kernel; nothing full-resolution is written
+                  "find_peaks": 2 * px_out * 24 * 4 / 1e6}
         _, hbm_peak, _ = measured_peaks()
         sr = {}
         for name, mb in alg_mb.items():
@@ -463,12 +464,15 @@ def run_ours(args):
                 gbs = mb / stages[name]                                                # MB / ms == GB/s
                 sr[name] = {"bound": "hbm", "algorithmic_MB_per_frame": round(mb, 2), "achieved_GBs": round(gbs, 1),
                             "frac_of_hbm_peak": round(gbs / hbm_peak, 3)}
-        if "smooth_nms" in sr:
-            sr["smooth_nms"]["note"] = ("bit-exact scipy arithmetic needs ~120 separately rounded float64 operations per "
-                                        "pixel (two 25-tap passes incl. tile halo, no FMA): ~0.105 ms/frame at the fp64 "
-                                        "pipe's ~18.9 T instr/s, i.e. this stage sits at the fp64 roofline, not the HBM one")
-        if "upsample_avg" in sr:
-            sr["upsample_avg"]["note"] = "24-28 fp32 FMAs per output element (4 scales x 6 composite taps): FMA-issue bound"
+        if "find_peaks" in sr:
+            sr["find_peaks"]["bound"] = "issue"
+            sr["find_peaks"]["note"] = ("round 1 wrote 210 MB of full-resolution maps per frame and read 66 MB back (upsample_avg 0.17 ms + "
+                                        "smooth_nms 0.11 ms); now the maps are evaluated per tile from the net outputs: DRAM traffic "
+                                        "= the algorithmic bytes (ncu: profiles/r02_ncu_prepost_c2_b8.csv), time = fp32 FMAs and index "
+                                        "arithmetic of the tiles that can hold a peak")
+        sr["paf_group"] = {"bound": "latency", "ms_per_frame": stages.get("paf_group"),
+                           "note": "PAF values are sampled on demand (10 samples x 2 channels per candidate pair) from the net "
+                                   "outputs: the 140 MB of full-resolution PAF planes per frame are never written"}
         line["stage_roofline"] = sr
         print(json.dumps(line), flush=True)
     if world > 1:
