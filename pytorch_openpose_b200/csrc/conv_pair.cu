@@ -36,6 +36,7 @@ struct QProb {
     int out_cstride, cout_store;
     int n_tiles_n, cin_chunks;
     int pair_begin, flags;
+    int tile_h;                  // 16, or 8 for small problems: one 16 x 8 half per CTA, twice the CTA pairs, half the K-loop depth
     int n_full_img;              // super-tiles per image whose two halves both hold pixels (they come first in the tile order)
     int noskip;                  // A/B switch: multiply empty halves too
     int vsplit;                  // 0: the two 128-pixel halves of a super-tile sit side by side (8 cols x 16 rows each),
@@ -47,6 +48,8 @@ struct alignas(64) PairParams {
     CUtensorMap tmW[kConvMaxProblems];
     QProb prob[kConvMaxProblems];
     int nprob, total_pairs, ks;
+    int resident;                // short-K layers (conv1_2: 3x3, 64 channels, one weight set): the 9 weight taps stay in shared
+                                 // memory for the whole kernel and ONE 24-column patch per tile serves all three dx
 };
 static_assert(sizeof(PairParams) <= 4000, "kernel parameter space");
 
@@ -55,7 +58,11 @@ struct QCfg {
     static constexpr int kPatchBytesMax = kPitch * (kTile + 6) * 128;      // 45056 (ks = 7)
     static constexpr int kNumPatch = 3;
     static constexpr int kBHalfBytes = (BLOCK_N / 2) * 128;                 // this CTA's half of a weight stage
-    static constexpr int kBStages = 8;
+    static constexpr int kBStages = BLOCK_N == 64 ? 9 : 8;     // 9: holds the 9 resident taps of a 3x3 layer (resident mode)
+    static constexpr int kResPitch = 24;                                   // resident mode: patch columns (18 used)
+    static constexpr int kResPatchBytes = kResPitch * (kTile + 2) * 128;   // 55296
+    static constexpr int kResPatchStride = (kNumPatch * kPatchBytesMax / 2) / 1024 * 1024;   // two buffers in the patch region
+    static_assert(kResPatchBytes <= kResPatchStride, "resident patch buffers");
     static constexpr int kTmemCols = kAccStages * kHalves * BLOCK_N;
     static constexpr int kNumBars = 2 * kNumPatch + 2 * kBStages + 2 * kAccStages;
     static constexpr int kBarBytes = kNumBars * 8 + 16;
@@ -122,9 +129,9 @@ __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, in
     c.pi = pi;
     c.img = img;
     c.x0 = txi * kTile;
-    c.y0 = tyi * kTile;
+    c.y0 = tyi * q.tile_h;
     c.n0 = nt * block_n;
-    const bool second = q.noskip || (q.vsplit ? (c.y0 + 8 < q.H) : (c.x0 + 8 < q.W));
+    const bool second = q.tile_h == kTile && (q.noskip || (q.vsplit ? (c.y0 + 8 < q.H) : (c.x0 + 8 < q.W)));
     c.halves = c.real ? (second ? 3 : 1) : 0;
     return c;
 }
@@ -190,17 +197,29 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
         // ================= patch (A) producer: own tile =================
         int pb = 0;
         uint32_t pphase = 0;
-        for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
-            const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
-            const int cin_chunks = p.prob[tc.pi].cin_chunks;
-            const CUtensorMap* tmA = &p.tmA[tc.pi];
-            for (int cc = 0; cc < cin_chunks; ++cc) {
-                for (int dx = 0; dx < ks; ++dx) {
-                    mbar_wait(&pempty[pb], pphase ^ 1, 10);
-                    if (rank == 0) mbar_arrive_expect_tx_elect(&pfull[pb], 2 * patch_bytes);
-                    tma_load_4d_2sm_elect(patches + pb * C::kPatchBytesMax, tmA, &pfull[pb], cc * 64, tc.x0 - pad + dx,
-                                          tc.y0 - pad, tc.img);
-                    if (++pb == C::kNumPatch) { pb = 0; pphase ^= 1; }
+        if (p.resident) {
+            for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
+                const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
+                mbar_wait(&pempty[pb], pphase ^ 1, 10);
+                if (rank == 0) mbar_arrive_expect_tx_elect(&pfull[pb], 2 * C::kResPatchBytes);
+                tma_load_4d_2sm_elect(patches + pb * C::kResPatchStride, &p.tmA[tc.pi], &pfull[pb], 0, tc.x0 - pad, tc.y0 - pad,
+                                      tc.img);
+                pb ^= 1;
+                if (pb == 0) pphase ^= 1;
+            }
+        } else {
+            for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
+                const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
+                const int cin_chunks = p.prob[tc.pi].cin_chunks;
+                const CUtensorMap* tmA = &p.tmA[tc.pi];
+                for (int cc = 0; cc < cin_chunks; ++cc) {
+                    for (int dx = 0; dx < ks; ++dx) {
+                        mbar_wait(&pempty[pb], pphase ^ 1, 10);
+                        if (rank == 0) mbar_arrive_expect_tx_elect(&pfull[pb], 2 * patch_bytes);
+                        tma_load_4d_2sm_elect(patches + pb * C::kPatchBytesMax, tmA, &pfull[pb], cc * 64, tc.x0 - pad + dx,
+                                              tc.y0 - pad, tc.img);
+                        if (++pb == C::kNumPatch) { pb = 0; pphase ^= 1; }
+                    }
                 }
             }
         }
@@ -208,18 +227,26 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
         // ================= weight (B) producer: this CTA's half of the N rows =================
         int bs = 0;
         uint32_t bphase = 0;
-        for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
-            const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
-            const int cin_chunks = p.prob[tc.pi].cin_chunks;
-            const CUtensorMap* tmW = &p.tmW[tc.pi];
-            for (int cc = 0; cc < cin_chunks; ++cc) {
-                for (int i = 0; i < ks * ks; ++i) {
-                    const int tap = (i % ks) * ks + (i / ks);              // dx outer, dy inner (matches the MMA walk)
-                    mbar_wait(&bempty[bs], bphase ^ 1, 11);
-                    if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[bs], 2 * C::kBHalfBytes);
-                    tma_load_2d_2sm_elect(bstages + bs * C::kBHalfBytes, tmW, &bfull[bs], (tap * cin_chunks + cc) * 64,
-                                          tc.n0 + rank * (BLOCK_N / 2));
-                    if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+        if (p.resident) {
+            // all taps once, tap t (row-major dy, dx) in stage t; every stage's barrier completes once and is never re-armed
+            for (int t = 0; t < ks * ks; ++t) {
+                if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[t], 2 * C::kBHalfBytes);
+                tma_load_2d_2sm_elect(bstages + t * C::kBHalfBytes, &p.tmW[0], &bfull[t], t * 64, rank * (BLOCK_N / 2));
+            }
+        } else {
+            for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
+                const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
+                const int cin_chunks = p.prob[tc.pi].cin_chunks;
+                const CUtensorMap* tmW = &p.tmW[tc.pi];
+                for (int cc = 0; cc < cin_chunks; ++cc) {
+                    for (int i = 0; i < ks * ks; ++i) {
+                        const int tap = (i % ks) * ks + (i / ks);              // dx outer, dy inner (matches the MMA walk)
+                        mbar_wait(&bempty[bs], bphase ^ 1, 11);
+                        if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[bs], 2 * C::kBHalfBytes);
+                        tma_load_2d_2sm_elect(bstages + bs * C::kBHalfBytes, tmW, &bfull[bs], (tap * cin_chunks + cc) * 64,
+                                              tc.n0 + rank * (BLOCK_N / 2));
+                        if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+                    }
                 }
             }
         }
@@ -229,6 +256,7 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
             constexpr uint32_t idesc = make_idesc_2sm(BLOCK_N);
             int pb = 0, bs = 0, acc = 0;
             uint32_t pphase = 0, bphase = 0, acc_phase = 0;
+            bool first_tile = true;
             for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
                 const TileCoord tc = decode_pair(p, pr, 0, BLOCK_N);
                 const QProb& q = p.prob[tc.pi];
@@ -240,6 +268,37 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 mbar_wait(&tempty[acc], acc_phase ^ 1, 12);               // both epilogues drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (kHalves * BLOCK_N);
+                if (p.resident) {
+                    // one 24-column patch: tap (dy, dx) of half h starts (dy * 24 + dx + 8 h) pixels into it (the swizzle
+                    // is a function of the absolute shared-memory address, so a start that is not atom aligned needs no
+                    // base offset); the weights of tap t wait in stage t
+                    mbar_wait(&pfull[pb], pphase, 13);
+                    tc_fence_after();
+                    const uint32_t patch_addr = smem_u32(patches + pb * C::kResPatchStride);
+                    for (int t = 0; t < ks * ks; ++t) {
+                        if (first_tile) {
+                            mbar_wait(&bfull[t], 0, 14);
+                            tc_fence_after();
+                        }
+                        const int dy = t / ks, dx = t - dy * ks;
+                        const uint64_t bdesc = make_desc(smem_u32(bstages + t * C::kBHalfBytes), 1024);
+#pragma unroll
+                        for (int h = 0; h < kHalves; ++h) {
+                            if (!(halves & (1 << h))) continue;
+                            const uint64_t adesc = make_desc(patch_addr + (uint32_t)((dy * C::kResPitch + dx + h * 8) * 128),
+                                                             C::kResPitch * 128);
+#pragma unroll
+                            for (int k = 0; k < 4; ++k) {
+                                umma_bf16_2sm_elect(d_tmem + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, accum[h]);
+                                accum[h] = 1;
+                            }
+                        }
+                    }
+                    first_tile = false;
+                    umma_commit_2sm_elect(&pempty[pb]);
+                    pb ^= 1;
+                    if (pb == 0) pphase ^= 1;
+                } else
                 for (int cc = 0; cc < q.cin_chunks; ++cc) {
                     for (int sh = 0; sh < ks; ++sh) {
                         mbar_wait(&pfull[pb], pphase, 13);                // both CTAs' patches have landed
@@ -402,6 +461,26 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
     P.nprob = (int)ops.size();
     P.ks = ops[0].ks;
     OPB_REQUIRE(P.ks == 3 || P.ks == 7, "conv_pair: kernel size 3 or 7");
+    // Small launches (a 640x480 frame at scale 0.5 gives 4 super-tiles per stage layer): when full 16x16 super-tiles
+    // would occupy at most a quarter of the CTA pairs the GPU holds, every CTA takes one 16x8 half instead -- twice the
+    // pairs, half the UMMAs per CTA, i.e. half the latency of the layer.  Pooling layers keep 16x16 (2x2 windows).
+    bool small = getenv("OPB_NO_HALF_TILES") == nullptr;
+    {
+        long full_pairs = 0;
+        for (const ConvOp& op : ops) {
+            full_pairs += (long)((cdiv(op.in.w, kTile) * cdiv(op.in.h, kTile) * op.in.n + 1) / 2) * (op.cout_pad / block_n);
+            if (op.pool) small = false;
+        }
+        if (full_pairs * 4 > num_sms / 2) small = false;
+    }
+    // resident mode (opt-in, OPB_CONV12_RESIDENT=1): a 3x3 layer on 64 input channels with one weight set and one 64-wide
+    // N tile (conv1_2 at every scale).  Measured on B200 at batch 8: 1.63 ms against 1.50 ms for the default path
+    // (654 vs 711 TFLOP/s): the layer is bound by shared-memory operand reads, not by L2 -> SM traffic, and the
+    // unaligned swizzle atoms of the single 24-column patch cost more wavefronts than the 2.7x smaller traffic saves.
+    bool resident = block_n == 64 && P.ks == 3 && !small && getenv("OPB_CONV12_RESIDENT") != nullptr;
+    for (const ConvOp& op : ops)
+        resident = resident && op.in.c == 64 && op.cout_pad == 64 && op.w == ops[0].w;
+    P.resident = resident ? 1 : 0;
     int pairs = 0;
     for (int i = 0; i < P.nprob; ++i) {
         const ConvOp& op = ops[i];
@@ -424,8 +503,9 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         q.out = op.out.ptr();
         q.bias = op.bias;
         q.H = H; q.W = W; q.N = N;
+        q.tile_h = small ? 8 : kTile;
         q.tiles_x = cdiv(W, kTile);
-        q.tiles_y = cdiv(H, kTile);
+        q.tiles_y = cdiv(H, q.tile_h);
         q.m_tiles = q.tiles_x * q.tiles_y * N;
         q.m_pairs = (q.m_tiles + 1) / 2;
         q.out_cstride = op.out.cstride;
@@ -438,11 +518,12 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
             // 128-pixel halves actually multiplied: side by side -> columns round up to 8 and rows to 16; stacked ->
             // columns to 16 and rows to 8 (e.g. 41x23: 48x32 vs 48x24; 82x46: 88x48 vs 96x48)
             static const char* force = getenv("OPB_PAIR_SPLIT");
-            const long side = (long)cdiv(W, 8) * 8 * cdiv(H, 16) * 16, stacked = (long)cdiv(W, 16) * 16 * cdiv(H, 8) * 8;
             static const char* noskip = getenv("OPB_PAIR_NOSKIP");
-            q.vsplit = force ? atoi(force) : (stacked < side ? 1 : 0);
+            const long side = (long)cdiv(W, 8) * 8 * cdiv(H, 16) * 16, stacked = (long)cdiv(W, 16) * 16 * cdiv(H, 8) * 8;
+            q.vsplit = small ? 1 : (resident ? 0 : (force ? atoi(force) : (stacked < side ? 1 : 0)));   // 24-column patches: side by side only
             q.noskip = noskip ? 1 : 0;
-            const bool edge = !q.noskip && (q.vsplit ? ((q.tiles_y - 1) * kTile + 8 >= H) : ((q.tiles_x - 1) * kTile + 8 >= W));
+            const bool edge = !small && !q.noskip &&
+                              (q.vsplit ? ((q.tiles_y - 1) * kTile + 8 >= H) : ((q.tiles_x - 1) * kTile + 8 >= W));
             q.n_full_img = q.tiles_x * q.tiles_y - (edge ? (q.vsplit ? q.tiles_x : q.tiles_y) : 0);
         }
         pairs += q.m_pairs * q.n_tiles_n;
@@ -450,7 +531,7 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         cuuint64_t adims[4] = {(cuuint64_t)op.in.c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
         cuuint64_t astr[3] = {(cuuint64_t)op.in.cstride * 2, (cuuint64_t)op.in.cstride * 2 * W,
                               (cuuint64_t)op.in.cstride * 2 * W * H};
-        cuuint32_t abox[4] = {64, (cuuint32_t)kPitch, (cuuint32_t)(kTile + P.ks - 1), 1};
+        cuuint32_t abox[4] = {64, (cuuint32_t)(resident ? QCfg<64>::kResPitch : kPitch), (cuuint32_t)(kTile + P.ks - 1), 1};
         tensor_map_encode_bf16(&P.tmA[i], op.in.ptr(), 4, adims, astr, abox);
         const cuuint64_t K = (cuuint64_t)op.ks * op.ks * op.in.c;
         cuuint64_t wdims[2] = {K, (cuuint64_t)op.cout_pad};

@@ -36,6 +36,8 @@ CASES = [
     (1, 12, 20, 512, 512, 3, True, False, False),    # conv4_2-like: K = 4608, 4 N tiles
     (3, 9, 7, 128, 512, 1, True, False, False),      # tiny maps smaller than the TMA box
     (1, 92, 164, 128, 128, 7, True, False, False),   # s=2.0 stage layer: 3 waves of tiles
+    (2, 50, 70, 64, 64, 3, True, False, False),      # conv1_2 shape class (see test_conv_pair_resident_variant)
+    (1, 184, 328, 64, 64, 3, True, True, False),     # conv1_2 at scale 0.5 with its fused pool
 ]
 
 
@@ -62,6 +64,24 @@ def test_conv_tc_matches_torch(case, impl):
     err = (out[..., :cout] - ref).abs().max().item()
     tol = 2e-3 * scale + (0 if fp32 else scale * 2 ** -8)
     assert err <= tol, "max err %.3e (scale %.3e, tol %.3e)" % (err, scale, tol)
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c[3] == 64 and c[4] == 64 and c[5] == 3],
+                         ids=lambda c: "n%d_%dx%d_p%d" % (c[0], c[1], c[2], int(c[7])))
+def test_conv_pair_resident_variant(case, monkeypatch):
+    """The opt-in conv1_2 variant of the CTA-pair kernel (weights resident in shared memory, one 24-column patch per
+    tile for all three dx; measured slower than the default, kept for A/B -- DESIGN.md section 6) obeys the same contract."""
+    from tests import gpu_util as G
+    monkeypatch.setenv("OPB_CONV12_RESIDENT", "1")
+    n, h, w, cin, cout, k, relu, pool, fp32 = case
+    g = torch.Generator().manual_seed(77)
+    x = (torch.randn(n, h, w, cin, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    wt = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    ref = _reference(x, wt, b, relu, pool)
+    out = G.conv2d(x, wt, b, relu, pool, fp32, impl=5).float()
+    scale = ref.abs().max().item()
+    assert (out[..., :cout] - ref).abs().max().item() <= 2e-3 * scale + scale * 2 ** -8
 
 
 def test_conv_direct_crosscheck():
