@@ -436,7 +436,7 @@ def run_ours(args):
 
     if rank == 0:
         total_frames = F * K * world
-        d2h = F * (4 * 25 + 2048 * 32 + 128 * 160)          # per frame: counts + eager candidate / subset rows
+        d2h = F * (32 * 4 + 2048 * 4 * 8 + 128 * 20 * 8)    # per frame: one FrameResults block (counts + first candidate / subset rows)
         line = {"metric": METRIC, "value": total_frames / (ms_dev * 1e-3), "unit": "frames/s", "n_gpus": world,
                 "steps": K, "warmup": Wm, "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
