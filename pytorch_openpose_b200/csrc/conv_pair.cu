@@ -14,6 +14,7 @@
 #include "opb_common.cuh"
 #include "tc_ptx.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 namespace opb {
 namespace {
@@ -35,7 +36,9 @@ struct QProb {
     int m_tiles, m_pairs;        // super-tiles of the problem, and pairs of them (rounded up)
     int out_cstride, cout_store;
     int n_tiles_n, cin_chunks;
-    int pair_begin, flags;
+    int pair_begin, flags;       // pair_begin: first index of the problem's full-cost pairs in the launch's pair order
+    int edge_begin;              // first index of its half-cost pairs (both tiles have an empty half), after ALL full-cost pairs
+    int n_full_pairs;            // pairs of the problem whose first tile has two occupied halves (x n_tiles_n in the order)
     int tile_h;                  // 16, or 8 for small problems: one 16 x 8 half per CTA, twice the CTA pairs, half the K-loop depth
     int n_full_img;              // super-tiles per image whose two halves both hold pixels (they come first in the tile order)
     int noskip;                  // A/B switch: multiply empty halves too
@@ -48,6 +51,8 @@ struct alignas(64) PairParams {
     CUtensorMap tmW[kConvMaxProblems];
     QProb prob[kConvMaxProblems];
     int nprob, total_pairs, ks;
+    int total_full;              // pairs [0, total_full) are full-cost, [total_full, total_pairs) half-cost: the round robin over
+                                 // CTA pairs then gives every cluster the same share of each, and the last round is a cheap one
     int resident;                // short-K layers (conv1_2: 3x3, 64 channels, one weight set): the 9 weight taps stay in shared
                                  // memory for the whole kernel and ONE 24-column patch per tile serves all three dx
 };
@@ -88,10 +93,15 @@ struct TileCoord {
     int halves;                  // bit h: half h of the super-tile holds at least one pixel of the image
 };
 __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, int rank, int block_n) {
-    int pi = 0;
-    while (pi + 1 < p.nprob && pr >= p.prob[pi + 1].pair_begin) ++pi;
+    int pi = 0, local;
+    if (pr < p.total_full) {
+        while (pi + 1 < p.nprob && pr >= p.prob[pi + 1].pair_begin) ++pi;
+        local = pr - p.prob[pi].pair_begin;
+    } else {
+        while (pi + 1 < p.nprob && pr >= p.prob[pi + 1].edge_begin) ++pi;
+        local = pr - p.prob[pi].edge_begin + p.prob[pi].n_full_pairs * p.prob[pi].n_tiles_n;
+    }
     const QProb& q = p.prob[pi];
-    const int local = pr - q.pair_begin;
     const int nt = local % q.n_tiles_n;
     const int mp = local / q.n_tiles_n;
     int mt = 2 * mp + rank;
@@ -512,7 +522,6 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         q.cout_store = op.cout_store;
         q.n_tiles_n = op.cout_pad / block_n;
         q.cin_chunks = op.in.c / 64;
-        q.pair_begin = pairs;
         q.flags = (op.relu ? FLAG_RELU : 0) | (op.out.elem == 4 ? FLAG_F32 : 0) | (op.pool ? FLAG_POOL : 0);
         {
             // 128-pixel halves actually multiplied: side by side -> columns round up to 8 and rows to 16; stacked ->
@@ -526,6 +535,8 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
                               (q.vsplit ? ((q.tiles_y - 1) * kTile + 8 >= H) : ((q.tiles_x - 1) * kTile + 8 >= W));
             q.n_full_img = q.tiles_x * q.tiles_y - (edge ? (q.vsplit ? q.tiles_x : q.tiles_y) : 0);
         }
+        // pairs whose first tile is a full one cost two halves, the rest one
+        q.n_full_pairs = std::min(q.m_pairs, (q.N * q.n_full_img + 1) / 2);
         pairs += q.m_pairs * q.n_tiles_n;
 
         cuuint64_t adims[4] = {(cuuint64_t)op.in.c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -538,6 +549,20 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         cuuint64_t wstr[1] = {K * 2};
         cuuint32_t wbox[2] = {64, (cuuint32_t)(block_n / 2)};
         tensor_map_encode_bf16(&P.tmW[i], (void*)op.w, 2, wdims, wstr, wbox);
+    }
+    // launch order: the full-cost pairs of every problem, then the half-cost pairs of every problem
+    {
+        int at = 0;
+        for (int i = 0; i < P.nprob; ++i) {
+            P.prob[i].pair_begin = at;
+            at += P.prob[i].n_full_pairs * P.prob[i].n_tiles_n;
+        }
+        P.total_full = at;
+        for (int i = 0; i < P.nprob; ++i) {
+            P.prob[i].edge_begin = at;
+            at += (P.prob[i].m_pairs - P.prob[i].n_full_pairs) * P.prob[i].n_tiles_n;
+        }
+        OPB_REQUIRE(at == pairs, "conv_pair: pair order");
     }
     P.total_pairs = pairs;
     L->tiles = pairs * 2;

@@ -87,7 +87,8 @@ __global__ void pose_select_kernel(const FramePost* __restrict__ frames, int n_f
             hb[k].x = b[0];
             hb[k].y = b[1];
             hb[k].w = b[2];
-            hb[k].valid = b[2] > 0;
+            // a box that is empty or leaves the frame is no box (util.handDetect never produces one)
+            hb[k].valid = b[2] > 0 && b[0] >= 0 && b[1] >= 0 && b[0] + b[2] <= W && b[1] + b[2] <= H;
         }
     }
     for (int k = 0; k < 2; ++k) {

@@ -243,7 +243,10 @@ def extract_motion_from_video(videopath, outpath, recpoint, body_estimation, han
     done = 0
     hand_pool = None
     native_hand = mode == "bodyhand" and pipelined and hasattr(hand_estimation, "submit") and hasattr(hand_estimation, "net")
-    if native_hand and type(body_estimation).__name__ == "Body" and os.environ.get("OPB_HOST_HANDS") is None:
+    from .body import Body
+    from .hand import Hand
+    if (native_hand and type(body_estimation) is Body and type(hand_estimation) is Hand
+            and os.environ.get("OPB_HOST_HANDS") is None):
         # both estimators are this package's: person selection, hand boxes, crops and the hand network stay on the
         # device, PoseMat is the only thing that comes back (motion.PoseEstimator)
         return _extract_bodyhand_on_device(src, outpath, body_estimation, hand_estimation, sessions, pinned, log, stats)

@@ -97,6 +97,28 @@ def test_ragged_hand_batch_equals_hand_on_every_crop():
         assert (pose[:, 18:, 2] > 0).any()                        # hands were really estimated
 
 
+def test_pose_single_frame_other_size_and_bad_boxes():
+    """est(frame) for one frame; a second frame size on the same estimators (the crop-size tables are rebuilt for the
+    larger frame); fixed boxes that leave the frame are treated as missing, not read out of bounds."""
+    from pytorch_openpose_b200 import Body, Hand, extract, motion
+    rng = np.random.default_rng(11)
+    body = Body(O.make_weights("body", 0), scale_search=[0.5])
+    hand = Hand(O.make_weights("hand", 5, "kaiming"), scale_search=[0.5, 1.0])
+    est = motion.PoseEstimator(body, hand)
+    small = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    pose = est(small)
+    assert pose.shape == (60, 3) and np.array_equal(pose[:18], extract.body_pose(*body(small))[0])
+    big = rng.integers(0, 256, (2, 300, 260, 3), dtype=np.uint8)
+    boxes = np.array([[[200, 10, 100], [0, 0, 260]],            # left: x + w > W -> missing; right: the largest possible box
+                      [[-5, 20, 50], [100, 250, 60]]], dtype=np.int32)      # negative x; y + w > H
+    est.submit_batch(big, fixed_boxes=boxes)
+    pose = est.collect()
+    assert not pose[0, 18:39].any() and not pose[1, 18:].any()
+    ref = np.zeros((60, 3))
+    extract._apply_hand(ref, hand(np.ascontiguousarray(big[0, 0:260, 0:260])), 0, 0, 260, False)
+    assert np.array_equal(pose[0, 39:], ref[39:])
+
+
 def test_bodyhand_video_job_on_device(tmp_path):
     """mode='bodyhand' with this package's own Body and Hand runs the device pipeline; its track equals the frame by
     frame host caller (random weights find nobody, so this pins the body rows and the plumbing; the hand path is pinned
