@@ -374,6 +374,8 @@ struct opb_session {
     };
     std::unique_ptr<PoseBuffers> pose;
     opb_session* pose_hand = nullptr;    // hand session of the pose batch in flight
+    std::vector<double> pose_hand_scales;
+    bool pose_fixed = false;
     ~opb_session() {
         plans.clear();
         net_plans.clear();
@@ -756,6 +758,10 @@ static bool grow_and_redo(opb_session* s, FramePlan* fp, int f, int appended, in
         cudaGraphExecDestroy(fp->graph);
         fp->graph = nullptr;
     }
+    if (fp->pose_graph) {
+        cudaGraphExecDestroy(fp->pose_graph);
+        fp->pose_graph = nullptr;
+    }
     const bool prof = s->prof.on;
     s->prof.on = false;
     body_post_range(s, fp, f, 1, fp->key.H, fp->key.W);
@@ -980,6 +986,29 @@ static void build_ragged_tables(opb_session* hs, const double* scales, int ns, i
     hs->ragged = std::move(r);
 }
 
+// the hand half of the pose pipeline, on the body session's stream: boxes from the body results (or the fixed ones already
+// in the pinned buffer), ragged crops -> hand CNN -> ragged post-processing -> PoseMat -> pinned host buffer
+static void pose_hand_enqueue(opb_session* bs, opb_session* hs, FramePlan* fp, FramePlan* hp, int n, int H, int W, bool fixed) {
+    cudaStream_t st = bs->stream;
+    const opb_session::Ragged& rg = *hs->ragged;
+    const int slots = 2 * n, tw = rg.tabs.wmax, nhs = rg.tabs.n_scales;
+    if (fixed)
+        OPB_CUDA(cudaMemcpyAsync(bs->pose->fixed, bs->pose->fixed_host, (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice, st));
+    pose_select_launch(fp->post_dev, n, H, W, fixed ? bs->pose->fixed : nullptr, bs->pose->pose, bs->pose->boxes, bs->pose->dims, st);
+    const float* src[kMaxScales];
+    int ho[kMaxScales], wo[kMaxScales];
+    for (int s = 0; s < nhs; ++s) {
+        preprocess_ragged_launch(fp->d_img, H, W, bs->pose->boxes, slots, hp->net->in_u8[s], rg.net_side[s], s, rg.tabs, st);
+        src[s] = hp->net->out_heat[s];
+        ho[s] = wo[s] = rg.net_side[s] / 8;
+    }
+    hp->net->run(st, nullptr);
+    upsample_ragged_launch(src, ho, wo, nhs, 24, 22, bs->pose->boxes, slots, rg.tabs, tw, hp->up_scratch, hp->heat_avg, st);
+    hand_peaks_ragged_launch(hp->heat_avg, slots, 22, bs->pose->dims, tw, 0.03, hp->hb, st);      // thre, src/hand.py:31
+    pose_finish_launch(bs->pose->boxes, hp->hb.peaks, n, bs->pose->pose, st);
+    OPB_CUDA(cudaMemcpyAsync(bs->pose->host, bs->pose->pose, (size_t)n * 180 * sizeof(double), cudaMemcpyDeviceToHost, st));
+}
+
 static void pose_submit(opb_session* bs, opb_session* hs, const uint8_t* imgs, int where, int n, int H, int W,
                         const double* bscales, int nbs, const double* hscales, int nhs, const int* fixed_boxes) {
     OPB_REQUIRE(bs->net->kind == OPB_NET_BODY && hs->net->kind == OPB_NET_HAND, "pose: a body session and a hand session");
@@ -1023,29 +1052,16 @@ static void pose_submit(opb_session* bs, opb_session* hs, const uint8_t* imgs, i
         memcpy(bs->pose->fixed_host, fixed_boxes, (size_t)n * 6 * sizeof(int));
         fixed_dev = bs->pose->fixed;
     }
-    const opb_session::Ragged& rg = *hs->ragged;
     // everything between the frame upload and the PoseMat copy is one launch sequence on one stream: replayed as a CUDA
     // graph from the third use on (re-captured when a buffer of either session, the hand plan or the box source changed)
     const uint64_t gen = bs->buffer_gen * 1000003ull + hs->buffer_gen * 7919ull + (uint64_t)(uintptr_t)hp +
-                         (uint64_t)(uintptr_t)rg.tabs.slab + (fixed_dev ? 1 : 0);
+                         (uint64_t)(uintptr_t)hs->ragged->tabs.slab + (fixed_dev ? 1 : 0);
+    bs->pose_hand_scales.assign(hscales, hscales + nhs);
+    bs->pose_fixed = fixed_dev != nullptr;
     run_or_replay_slot(bs, GraphSlot{fp->pose_graph, fp->pose_gen, fp->pose_uses}, gen, [&] {
         run_front(bs, fp, n, H, W);
         body_post_enqueue(bs, fp, n, H, W);
-        if (fixed_dev)
-            OPB_CUDA(cudaMemcpyAsync(bs->pose->fixed, bs->pose->fixed_host, (size_t)n * 6 * sizeof(int), cudaMemcpyHostToDevice, st));
-        pose_select_launch(fp->post_dev, n, H, W, fixed_dev, bs->pose->pose, bs->pose->boxes, bs->pose->dims, st);
-        const float* src[kMaxScales];
-        int ho[kMaxScales], wo[kMaxScales];
-        for (int s = 0; s < nhs; ++s) {
-            preprocess_ragged_launch(fp->d_img, H, W, bs->pose->boxes, slots, hp->net->in_u8[s], rg.net_side[s], s, rg.tabs, st);
-            src[s] = hp->net->out_heat[s];
-            ho[s] = wo[s] = rg.net_side[s] / 8;
-        }
-        hp->net->run(st, nullptr);
-        upsample_ragged_launch(src, ho, wo, nhs, 24, 22, bs->pose->boxes, slots, rg.tabs, tw, hp->up_scratch, hp->heat_avg, st);
-        hand_peaks_ragged_launch(hp->heat_avg, slots, 22, bs->pose->dims, tw, 0.03, hp->hb, st);      // thre, src/hand.py:31
-        pose_finish_launch(bs->pose->boxes, hp->hb.peaks, n, bs->pose->pose, st);
-        OPB_CUDA(cudaMemcpyAsync(bs->pose->host, bs->pose->pose, (size_t)n * 180 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        pose_hand_enqueue(bs, hs, fp, hp, n, H, W, fixed_dev != nullptr);
     });
     OPB_CUDA(cudaEventRecord(bs->done, st));
     bs->net->ctx->launches += fp->launches_per_frame + nhs + hp->net->kernel_launches + (nhs + 1) + 6 + 2;
@@ -1354,15 +1370,29 @@ int opb_pose_wait(opb_session* body_s, double* pose_mats, int* frame_status) {
         // body results first: they report the overflow / IndexError conditions of every frame
         std::vector<int> st(body_s->n_frames);
         OPB_CUDA(cudaEventSynchronize(body_s->done));
+        FramePlan* fp = body_s->active;
+        bool grew = false;
         for (int f = 0; f < body_s->n_frames; ++f) {
             const HostResults* h = body_s->host + f;
+            // a frame that overflowed its peak / pair / connection / person buffers gets larger ones and its body
+            // post-processing is repeated (like opb_body_wait_batch); the hand half is then repeated for the batch
+            for (int attempt = 0; attempt < 12; ++attempt) {
+                const FramePost& bp = fp->post[f];
+                if (h->counts[0] <= bp.pb.capacity && !(h->counts[21] & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow))) break;
+                if (!grow_and_redo(body_s, fp, f, h->counts[0], h->counts[21])) break;
+                grew = true;
+            }
             const int status = h->counts[21];
-            const FramePost& bp = body_s->active->post[f];
-            if (h->counts[0] > bp.pb.capacity || (status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow)))
-                throw Error(OPB_ERR_CAPACITY, "a frame overflowed the body result buffers: use opb_body_submit_batch for it");
+            if (h->counts[0] > fp->post[f].pb.capacity || (status & (kStPairOverflow | kStConnOverflow | kStSubsetOverflow)))
+                throw Error(OPB_ERR_CAPACITY, "a frame overflowed the body result buffers (status " + std::to_string(status) + ")");
             st[f] = (status & kStIndexError) ? OPB_ERR_SUBSET_INDEX : OPB_OK;
             if (frame_status) frame_status[f] = st[f];
             if (st[f] != OPB_OK && rc == OPB_OK) rc = st[f];
+        }
+        if (grew) {
+            opb_session* hs = body_s->pose_hand;
+            pose_hand_enqueue(body_s, hs, fp, hs->active, body_s->n_frames, fp->key.H, fp->key.W, body_s->pose_fixed);
+            OPB_CUDA(cudaStreamSynchronize(body_s->stream));
         }
         memcpy(pose_mats, body_s->pose->host, (size_t)body_s->n_frames * 180 * sizeof(double));
         if (rc == OPB_ERR_SUBSET_INDEX)

@@ -140,3 +140,35 @@ def test_bodyhand_video_job_on_device(tmp_path):
         assert ok
         pose, _, _ = motion.pose_mat_every_frame(frame, body, hand, "bodyhand")
         assert np.array_equal(mat[i], pose)
+
+
+def test_pose_pipeline_grows_result_buffers():
+    """Frames whose peaks / limb pairs / person rows overflow the (here: tiny) initial buffers: the device pipeline grows
+    them, repeats the body post-processing of those frames and the hand half of the batch, and still equals the host
+    pipeline -- also on the following calls (re-captured graph)."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, cv2
+from oracle import openpose_oracle as O
+from pytorch_openpose_b200 import Body, Hand, motion
+rng = np.random.default_rng(21)
+frames = np.stack([cv2.GaussianBlur(rng.integers(0, 256, (169, 439, 3), dtype=np.uint8), (0, 0), 1.5) for _ in range(3)])
+body = Body(O.make_weights("body", 2, "kaiming"), scale_search=[1.0])
+hand = Hand(O.make_weights("hand", 5, "kaiming"), scale_search=[0.5, 1.0])
+est = motion.PoseEstimator(body, hand)
+persons = 0
+for rep in range(4):
+    pose = est(frames)
+    for f in range(3):
+        ref, cand, sub = motion.pose_mat_every_frame(frames[f], body, hand, "bodyhand")
+        assert len(cand) > 64, len(cand)
+        persons += len(sub)
+        assert np.array_equal(pose[f], ref), (rep, f)
+print("POSE-GROWTH-OK persons", persons)
+'''
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, OPB_TEST_SMALL_BUFFERS="1", PYTHONPATH=root)
+    r = subprocess.run([sys.executable, "-c", code], env=env, cwd=root, capture_output=True, text=True, timeout=600)
+    assert "POSE-GROWTH-OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
