@@ -311,6 +311,43 @@ struct Builder {
         plan->kernel_launches += 1;
         return true;
     }
+    // conv5_4 + conv5_5 of stage 1 (hand: conv6_1 + conv6_2) as one fused launch with the 512-channel intermediate kept on
+    // the SM (conv_tail.cu, wide variant); OPB_NO_FUSE_WIDE=1: two grouped launches through HBM.
+    bool wide_tail_group(const std::vector<std::string>& n4, const std::vector<std::string>& n5,
+                         const std::vector<TensorView>& ins, const std::vector<TensorView>& outs) {
+        static const bool fuse = getenv("OPB_NO_FUSE_WIDE") == nullptr && getenv("OPB_NO_FUSE_TAILS") == nullptr;
+        if (!fuse) return false;
+        std::vector<TailOp> ops;
+        double gf = 0;
+        for (size_t i = 0; i < n4.size(); ++i) {
+            const DevLayer& a = net->dev.at(n4[i]);
+            const DevLayer& b = net->dev.at(n5[i]);
+            if (a.k != 1 || b.k != 1 || a.cin_dev != 128 || a.cout_pad != 512 || a.cout_store != 512 || !a.relu ||
+                b.cin_dev != 512 || b.cout_pad != 64)
+                return false;
+            TailOp op;
+            op.in = ins[i];
+            op.out = outs[i];
+            op.w1 = a.w; op.b1 = a.bias;
+            op.w2 = b.w; op.b2 = b.bias;
+            op.cout_pad2 = b.cout_pad;
+            op.cout_store = b.cout_store;
+            op.relu2 = b.relu;
+            ops.push_back(op);
+        }
+        if (!conv_tail_wide_supported(ops)) return false;
+        for (size_t i = 0; i < n4.size(); ++i) {
+            gf += add_flops(n4[i], ins[i]);
+            gf += add_flops(n5[i], ins[i]);
+        }
+        ConvLaunch* L = conv_tail_wide_plan(ops, net->ctx->num_sms);
+        plan->launches.push_back(L);
+        plan->steps.push_back([L](cudaStream_t s) { conv_tc_plan_run(L, s); });
+        plan->step_names.push_back("conv_tail:" + n4[0]);
+        plan->step_gflop.push_back(gf);
+        plan->kernel_launches += 1;
+        return true;
+    }
     // algorithmic FLOPs of one layer on one input (un-padded channel counts)
     double add_flops(const std::string& name, const TensorView& in) {
         for (const auto& s : layer_specs(net->kind))
@@ -472,8 +509,20 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
         branch_layer("conv5_1_CPM_L%d", 0, both(feat), pa, false);
         branch_layer("conv5_2_CPM_L%d", 0, pa, pb, false);
         branch_layer("conv5_3_CPM_L%d", 0, pb, pa, false);
-        branch_layer("conv5_4_CPM_L%d", 0, pa, wide, false);
-        branch_layer("conv5_5_CPM_L%d", 0, wide, slices(false), false);
+        {
+            std::vector<std::string> n4(2 * S), n5(2 * S);
+            for (int s = 0; s < S; ++s)
+                for (int b = 0; b < 2; ++b) {
+                    snprintf(buf, sizeof buf, "conv5_4_CPM_L%d", b + 1);
+                    n4[2 * s + b] = buf;
+                    snprintf(buf, sizeof buf, "conv5_5_CPM_L%d", b + 1);
+                    n5[2 * s + b] = buf;
+                }
+            if (!B.wide_tail_group(n4, n5, pa, slices(false))) {
+                branch_layer("conv5_4_CPM_L%d", 0, pa, wide, false);
+                branch_layer("conv5_5_CPM_L%d", 0, wide, slices(false), false);
+            }
+        }
         // stages 2..6 (src/model.py:69-87)
         for (int st = 2; st <= 6; ++st) {
             branch_layer("Mconv1_stage%d_L%d", st, both(cat), pa, true);
@@ -514,8 +563,11 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
         auto layer = [&](const std::string& name, const std::vector<TensorView>& ins, const std::vector<TensorView>& outs) {
             B.conv_group(std::vector<std::string>(S, name), ins, outs, false);
         };
-        layer("conv6_1_CPM", feat, wide);
-        layer("conv6_2_CPM", wide, heat_slice);
+        if (!B.wide_tail_group(std::vector<std::string>(S, "conv6_1_CPM"), std::vector<std::string>(S, "conv6_2_CPM"), feat,
+                               heat_slice)) {
+            layer("conv6_1_CPM", feat, wide);
+            layer("conv6_2_CPM", wide, heat_slice);
+        }
         for (int st = 2; st <= 6; ++st) {
             auto nm = [&](int i) {
                 snprintf(buf, sizeof buf, "Mconv%d_stage%d", i, st);

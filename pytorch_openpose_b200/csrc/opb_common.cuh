@@ -86,6 +86,9 @@ struct TailOp {
 };
 bool conv_tail_supported(const std::vector<TailOp>& ops);
 ConvLaunch* conv_tail_plan(const std::vector<TailOp>& ops, int num_sms);
+// the same with a 512-channel intermediate in four slices (conv5_4 -> conv5_5, conv6_1 -> conv6_2): w1 [512][128], w2 [64][512]
+bool conv_tail_wide_supported(const std::vector<TailOp>& ops);
+ConvLaunch* conv_tail_wide_plan(const std::vector<TailOp>& ops, int num_sms);
 inline void conv_tc_plan_run(const ConvLaunch* L, cudaStream_t stream) { L->run(stream); }
 inline void conv_tc_plan_free(ConvLaunch* L) { delete L; }
 void tensor_map_encode_bf16(CUtensorMap* tm, void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
