@@ -203,10 +203,12 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
     tc_fence_after();
     const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
+    pdl_launch_dependents();                            // the next layer may start its prologue (it waits before touching data)
     if (warp == 6) {
         // ================= patch (A) producer: own tile =================
         int pb = 0;
         uint32_t pphase = 0;
+        pdl_wait();                                     // the activations are the previous kernel's output (weights are not)
         if (p.resident) {
             for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
                 const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
@@ -451,7 +453,9 @@ void launch_pair(const PairLaunch& L, cudaStream_t stream) {
     if (first_use_on_device(attr)) {
         OPB_CUDA(cudaFuncSetAttribute(conv_pair_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, QCfg<BN>::kSmemBytes));
     }
-    conv_pair_kernel<BN><<<L.grid, kThreads, QCfg<BN>::kSmemBytes, stream>>>(L.params);
+    // programmatic dependent launch: the kernel's prologue and its weight loads overlap the previous kernel's tail; the
+    // patch producer executes griddepcontrol.wait before the first activation load
+    launch_pdl(conv_pair_kernel<BN>, L.grid, kThreads, QCfg<BN>::kSmemBytes, stream, L.params);
 }
 
 void PairLaunch::run(cudaStream_t stream) const {

@@ -118,6 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tail_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -128,6 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tail_kernel(const __grid_con
         }
         int stage = 0;
         uint32_t phase = 0;
+        pdl_wait();                     // weights are on their way; the activations are the previous kernel's output
         for (int i = 0; i < n_my; ++i) {
             int pi, pix0;
             decode(p, g, cta + i * ctas, pi, pix0);
@@ -354,9 +356,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tail_wide_kernel(const __gri
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
 
     if (warp == 0) {
         // ================= TMA producer =================
+        pdl_wait();                     // the activations are the previous kernel's output
         for (int i = 0; i < n_my; ++i) {
             int pi, pix0;
             decode_wide(p, g, cta + i * ctas, pi, pix0);
@@ -503,7 +507,7 @@ struct WideLaunch : ConvLaunch {
         static bool attr[64] = {};
         if (first_use_on_device(attr))
             OPB_CUDA(cudaFuncSetAttribute(conv_tail_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWideSmem));
-        conv_tail_wide_kernel<<<grid, kThreads, kWideSmem, stream>>>(params);
+        launch_pdl(conv_tail_wide_kernel, grid, kThreads, kWideSmem, stream, params);
         OPB_CUDA(cudaGetLastError());
     }
 };
@@ -515,7 +519,7 @@ struct TailLaunch : ConvLaunch {
         static bool attr[64] = {};
         if (first_use_on_device(attr))
             OPB_CUDA(cudaFuncSetAttribute(conv_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        conv_tail_kernel<<<grid, kThreads, kSmemBytes, stream>>>(params);
+        launch_pdl(conv_tail_kernel, grid, kThreads, kSmemBytes, stream, params);
         OPB_CUDA(cudaGetLastError());
     }
 };

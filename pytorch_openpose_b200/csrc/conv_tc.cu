@@ -137,11 +137,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int taps = p.ks * p.ks;
     const int pad = p.ks >> 1;
 
+    pdl_launch_dependents();
     if (warp == 0) {
         // ================= TMA producer =================
         {   // all 32 lanes walk the loop (warp-uniform); one elected lane issues each async op
             int stage = 0;
             uint32_t phase = 0;
+            pdl_wait();                 // programmatic dependent launch: the prologue above overlapped the predecessor
             for (int t = blockIdx.x; t < p.total_tiles; t += gridDim.x) {
                 const TileCoord tc = decode_tile(p, t, BLOCK_N);
                 const int cin_chunks = p.prob[tc.pi].cin_chunks;
@@ -422,9 +424,9 @@ static void conv_tc_run(const TapLaunch& L, cudaStream_t stream) {
                                       Cfg<64>::kSmemBytes));
     }
     if (L.block_n == 128)
-        conv_tc_kernel<128><<<L.grid, kThreads, Cfg<128>::kSmemBytes, stream>>>(L.params);
+        launch_pdl(conv_tc_kernel<128>, L.grid, kThreads, Cfg<128>::kSmemBytes, stream, L.params);
     else
-        conv_tc_kernel<64><<<L.grid, kThreads, Cfg<64>::kSmemBytes, stream>>>(L.params);
+        launch_pdl(conv_tc_kernel<64>, L.grid, kThreads, Cfg<64>::kSmemBytes, stream, L.params);
     OPB_CUDA(cudaGetLastError());
 }
 

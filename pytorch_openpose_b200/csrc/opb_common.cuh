@@ -12,6 +12,7 @@
 #include <stdexcept>
 #include <memory>
 #include <cstring>
+#include <cstdlib>
 
 #include "../../include/openpose_b200.h"
 
@@ -109,6 +110,25 @@ inline bool first_use_on_device(bool (&flags)[64]) {
     if (flags[dev]) return false;
     flags[dev] = true;
     return true;
+}
+
+// Programmatic dependent launch (tc_ptx.cuh::pdl_wait): the kernel may start while its predecessor in the stream still
+// runs; ONLY for kernels that execute griddepcontrol.wait before they touch the predecessor's output.  OPB_NO_PDL=1
+// launches plainly.
+template <typename Params>
+inline void launch_pdl(void (*kernel)(Params), int grid, int block, size_t smem, cudaStream_t stream, const Params& params) {
+    static const bool pdl = getenv("OPB_NO_PDL") == nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    OPB_CUDA(cudaLaunchKernelEx(&cfg, kernel, params));
 }
 
 // ---- pre/post processing (prepost.cu)

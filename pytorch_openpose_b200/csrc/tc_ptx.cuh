@@ -290,6 +290,13 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t rank
         : "memory");
 }
 // kind::f16 instruction descriptor for the pair: D=f32, A=B=bf16, K-major, M=256, N=n
+// ---- programmatic dependent launch: a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream still runs; pdl_wait() blocks until the predecessor has completed and its writes
+// are visible -- everything a kernel does before it (barrier init, TMEM allocation, tensor-map prefetch, weight loads)
+// overlaps the predecessor's tail.  pdl_launch_dependents() lets the successor start its own prologue.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __host__ __device__ constexpr uint32_t make_idesc_2sm(int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 }
