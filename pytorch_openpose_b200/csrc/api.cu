@@ -308,6 +308,7 @@ static void alloc_body_post(DevPool& pool, FramePost& fp, int* counters, FrameRe
     fp.lb.rows_global = subset_cap > kSubsetRowsShared ? pool.alloc_t<double>((size_t)subset_cap * kSubsetRowStride) : nullptr;
     fp.lb.order = pool.alloc_t<int>((size_t)19 * pair_cap);
     fp.lb.owner_global = pool.alloc_t<int4>((size_t)peak_cap);
+    fp.lb.claim_global = subset_cap > kSubsetRowsShared ? pool.alloc_t<int>((size_t)subset_cap) : nullptr;
     fp.result = result;
 }
 

@@ -212,6 +212,7 @@ struct LimbBuffers {
     double* subset;           // [subset_capacity][20]
     double* rows_global;      // [subset_capacity][kSubsetRowStride] assembly work rows when they do not fit shared memory, else null
     int4* owner_global;       // [max_part] rows holding each candidate (assembly; shared memory is used for small frames)
+    int* claim_global;        // [subset_capacity] row claims of the assembly rounds when the rows live in global memory, else null
     int* subset_count;        // [1] rows after pruning
     int* status;              // [4]: bit flags (overflow / IndexError edge), rows before pruning, ...
     int* order;               // [19][pair_capacity] sorted order of the survivors

@@ -281,21 +281,26 @@ __device__ __forceinline__ void two_smallest(const int e[6], int& found, int& j1
 
 __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restrict__ frames) {
     constexpr int RS = kSubsetRowStride;
-    extern __shared__ double rows_shared[];          // [min(subset_capacity, kSubsetRowsShared)][RS], then the owner lists
+    extern __shared__ double rows_shared[];          // [min(subset_capacity, kSubsetRowsShared)][RS], owner lists, row claims
     const FramePost& fr = frames[blockIdx.x];
     const double* __restrict__ cand = fr.pb.candidates;
     const LimbBuffers& lb = fr.lb;
     double* rows = lb.rows_global ? lb.rows_global : rows_shared;
     const int n_cand = min(fr.pb.part_begin[18], fr.pb.capacity);
-    const size_t rows_bytes = ((size_t)(lb.rows_global ? 0 : min(lb.subset_capacity, kSubsetRowsShared)) * RS * 8 + 15) & ~(size_t)15;
-    int4* own = n_cand <= kOwnerShared ? (int4*)((uint8_t*)rows_shared + rows_bytes) : lb.owner_global;
+    const int rows_in_smem = lb.rows_global ? 0 : min(lb.subset_capacity, kSubsetRowsShared);
+    const size_t rows_bytes = ((size_t)rows_in_smem * RS * 8 + 15) & ~(size_t)15;
+    int4* own_shared = (int4*)((uint8_t*)rows_shared + rows_bytes);
+    int4* own = n_cand <= kOwnerShared ? own_shared : lb.owner_global;
+    // claim[row]: lowest lane of the current round that touches the row (INT_MAX when idle)
+    int* claim = lb.rows_global ? lb.claim_global : (int*)(own_shared + kOwnerShared);
     const int lane = threadIdx.x;
     int nrows = 0;
     bool fail = false, own_overflow = false;
     for (int t = lane; t < n_cand; t += 32) own[t] = make_int4(-1, -1, -1, 0);
+    for (int t = lane; t < lb.subset_capacity; t += 32) claim[t] = 0x7fffffff;
 
     // connections are staged through shared memory in chunks (coalesced loads, candidate scores gathered in
-    // parallel): the sequential merge below then never waits on global memory
+    // parallel): the walk below then never waits on global memory
     constexpr int CH = 256;
     __shared__ double sconn[CH][5];                  // idA, idB, limb score, score(candA), score(candB)
     for (int k = 0; k < kLimbs && !fail; ++k) {
@@ -303,6 +308,92 @@ __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restric
         if (ncon < 0) continue;                      // special_k
         const int ia = c_limb_a[k], ib = c_limb_b[k];
         const double* conn = lb.conn + (size_t)k * lb.conn_capacity * 5;
+
+        // one connection, by the whole warp, exactly as the reference's loop body (src/body.py:166-202)
+        auto serial_one = [&](int c) {
+            const double idA = sconn[c][0], idB = sconn[c][1], limb_score = sconn[c][2];
+            const double scoreA = sconn[c][3], scoreB = sconn[c][4];
+            const int a_id = (int)idA, b_id = (int)idB;
+            int found, j1, j2;
+            const int4 oa = own[a_id], ob = own[b_id];
+            if ((oa.w | ob.w) == 0) {
+                const int e[6] = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z};
+                two_smallest(e, found, j1, j2);
+            } else {                                 // a candidate held by more than three rows: scan
+                found = 0;
+                j1 = j2 = -1;
+                for (int base = 0; base < nrows; base += 32) {
+                    const int j = base + lane;
+                    const bool m = j < nrows && rows[j * RS + 20] == 0.0 &&
+                                   (rows[j * RS + ia] == idA || rows[j * RS + ib] == idB);
+                    unsigned mask = __ballot_sync(0xffffffffu, m);
+                    while (mask) {
+                        const int bpos = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        if (found == 0) j1 = base + bpos;
+                        else if (found == 1) j2 = base + bpos;
+                        ++found;
+                    }
+                }
+            }
+            if (found > 2) {                         // reference: IndexError at src/body.py:173
+                fail = true;
+                if (lane == 0) atomicOr(lb.status, ST_INDEX_ERROR);
+                return;
+            }
+            bool extend = found == 1;                // "row j1 gets candidate B" (also the overlapping found == 2 case)
+            if (found == 2) {
+                // disjoint?  (membership == 2 nowhere over the 18 part slots)
+                const bool both = lane < 18 && rows[j1 * RS + lane] >= 0.0 && rows[j2 * RS + lane] >= 0.0;
+                const bool overlap = __ballot_sync(0xffffffffu, both) != 0;
+                if (!overlap) {
+                    // subset[j1][:-2] += subset[j2][:-2] + 1 ; tails summed ; + limb score ; row j2 deleted
+                    double moved = -1.0;
+                    if (lane < 18) {
+                        moved = rows[j2 * RS + lane];
+                        rows[j1 * RS + lane] = rows[j1 * RS + lane] + (moved + 1.0);
+                    }
+                    if (lane == 18) rows[j1 * RS + 18] = (rows[j1 * RS + 18] + rows[j2 * RS + 18]) + limb_score;
+                    if (lane == 19) rows[j1 * RS + 19] = rows[j1 * RS + 19] + rows[j2 * RS + 19];
+                    if (lane == 20) rows[j2 * RS + 20] = 1.0;                     // tombstone
+                    __syncwarp();
+                    if (lane < 18 && moved >= 0.0) owner_replace(own, (int)moved, j2, j1);
+                    __syncwarp();
+                } else {
+                    extend = true;
+                }
+            } else if (found == 0 && k < 17) {
+                if (nrows >= lb.subset_capacity) {
+                    fail = true;
+                    if (lane == 0) atomicOr(lb.status, ST_SUBSET_OVERFLOW);
+                    return;
+                }
+                if (lane < 18) rows[nrows * RS + lane] = lane == ia ? idA : (lane == ib ? idB : -1.0);
+                if (lane == 18) rows[nrows * RS + 18] = ((0.0 + scoreA) + scoreB) + limb_score;
+                if (lane == 19) rows[nrows * RS + 19] = 2.0;
+                if (lane == 20) rows[nrows * RS + 20] = 0.0;
+                if (lane == 0) {
+                    owner_add(own, a_id, nrows, own_overflow);
+                    owner_add(own, b_id, nrows, own_overflow);
+                }
+                ++nrows;
+            }
+            if (extend && lane == 0) {
+                // found == 1 (src/body.py:176-181) and the overlapping found == 2 case (:189-193)
+                const double old = rows[j1 * RS + ib];
+                if (found == 2 || old != idB) {
+                    if (old != idB) {
+                        if (old >= 0.0) owner_remove(own, (int)old, j1);          // overwritten, as in the reference
+                        owner_add(own, b_id, j1, own_overflow);
+                    }
+                    rows[j1 * RS + ib] = idB;
+                    rows[j1 * RS + 19] += 1.0;
+                    rows[j1 * RS + 18] += scoreB + limb_score;
+                }
+            }
+            __syncwarp();
+        };
+
         for (int base_c = 0; base_c < ncon && !fail; base_c += CH) {
             const int nch = min(CH, ncon - base_c);
             __syncwarp();
@@ -316,94 +407,95 @@ __global__ void __launch_bounds__(32) assemble_kernel(const FramePost* __restric
                 sconn[t][4] = cand[(size_t)(int)b * 4 + 2];
             }
             __syncwarp();
-            for (int c = 0; c < nch && !fail; ++c) {
-                const double idA = sconn[c][0], idB = sconn[c][1], limb_score = sconn[c][2];
-                const double scoreA = sconn[c][3], scoreB = sconn[c][4];
-                const int a_id = (int)idA, b_id = (int)idB;
-                // rows j with subset[j][indexA] == partAs[i] or subset[j][indexB] == partBs[i] (every lane computes the
-                // same answer: the warp stays converged, nothing to exchange)
-                int found, j1, j2;
-                const int4 oa = own[a_id], ob = own[b_id];
-                if ((oa.w | ob.w) == 0) {
-                    const int e[6] = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z};
-                    two_smallest(e, found, j1, j2);
-                } else {
-                    found = 0;
-                    j1 = j2 = -1;
-                    for (int base = 0; base < nrows; base += 32) {
-                        const int j = base + lane;
-                        const bool m = j < nrows && rows[j * RS + 20] == 0.0 &&
-                                       (rows[j * RS + ia] == idA || rows[j * RS + ib] == idB);
-                        unsigned mask = __ballot_sync(0xffffffffu, m);
-                        while (mask) {
-                            const int bpos = __ffs(mask) - 1;
-                            mask &= mask - 1;
-                            if (found == 0) j1 = base + bpos;
-                            else if (found == 1) j2 = base + bpos;
-                            ++found;
+            // 32 connections at a time, one per lane.  Connections of one limb have distinct A and distinct B candidates,
+            // so two of them interact only through a row both touch.  Every pending lane claims its rows (atomicMin of
+            // the lane index); a lane that holds all its claims has no earlier pending connection on its rows and runs
+            // now -- the simple cases (new row, plain extension) in parallel, merges / overwrites / owner-list overflows
+            // one at a time by the whole warp -- the others wait for the next round.  New rows never conflict and get
+            // their indices from a prefix count in connection order, so the result is the sequential walk's, bit for bit.
+            for (int g0 = 0; g0 < nch && !fail; g0 += 32) {
+                const int c = g0 + lane;
+                unsigned pending = __ballot_sync(0xffffffffu, c < nch);
+                while (pending && !fail) {
+                    const bool mine = (pending >> lane) & 1u;
+                    int found = 0, j1 = -1, j2 = -1, a_id = 0, b_id = 0;
+                    bool complex_case = false, noop = false, scan = false;
+                    double idB = 0.0;
+                    if (mine) {
+                        a_id = (int)sconn[c][0];
+                        idB = sconn[c][1];
+                        b_id = (int)idB;
+                        const int4 oa = own[a_id], ob = own[b_id];
+                        if ((oa.w | ob.w) != 0) {
+                            complex_case = scan = true;      // owner lists overflowed: the rows are only found by a scan
+                        } else {
+                            const int e[6] = {oa.x, oa.y, oa.z, ob.x, ob.y, ob.z};
+                            two_smallest(e, found, j1, j2);
+                            if (found >= 2) complex_case = true;
+                            if (found == 1) {
+                                const double old = rows[j1 * RS + ib];
+                                noop = old == idB;
+                                if (!noop && old >= 0.0) complex_case = true;        // overwrite: owner_remove on a shared entry
+                            }
                         }
                     }
-                }
-                if (found > 2) {                         // reference: IndexError at src/body.py:173
-                    fail = true;
-                    if (lane == 0) atomicOr(lb.status, ST_INDEX_ERROR);
-                    break;
-                }
-                bool extend = found == 1;                // "row j1 gets candidate B" (also the overlapping found == 2 case)
-                if (found == 2) {
-                    // disjoint?  (membership == 2 nowhere over the 18 part slots)
-                    const bool both = lane < 18 && rows[j1 * RS + lane] >= 0.0 && rows[j2 * RS + lane] >= 0.0;
-                    const bool overlap = __ballot_sync(0xffffffffu, both) != 0;
-                    if (!overlap) {
-                        // subset[j1][:-2] += subset[j2][:-2] + 1 ; tails summed ; + limb score ; row j2 deleted
-                        double moved = -1.0;
-                        if (lane < 18) {
-                            moved = rows[j2 * RS + lane];
-                            rows[j1 * RS + lane] = rows[j1 * RS + lane] + (moved + 1.0);
-                        }
-                        if (lane == 18) rows[j1 * RS + 18] = (rows[j1 * RS + 18] + rows[j2 * RS + 18]) + limb_score;
-                        if (lane == 19) rows[j1 * RS + 19] = rows[j1 * RS + 19] + rows[j2 * RS + 19];
-                        if (lane == 20) rows[j2 * RS + 20] = 1.0;                     // tombstone
-                        __syncwarp();
-                        // candidates of the deleted row now belong to row j1 (one lane at a time: two parts of the row
-                        // never share a candidate, but the owner entries are read-modify-write)
-                        if (lane < 18 && moved >= 0.0) owner_replace(own, (int)moved, j2, j1);
-                        __syncwarp();
-                    } else {
-                        extend = true;
+                    // a lane on the scan path cannot name its rows: it may only run when it is the lowest pending lane
+                    const unsigned scan_lanes = __ballot_sync(0xffffffffu, mine && scan);
+                    if (mine && j1 >= 0 && found <= 2) {
+                        atomicMin(&claim[j1], lane);
+                        if (found == 2) atomicMin(&claim[j2], lane);
                     }
-                } else if (found == 0 && k < 17) {
-                    if (nrows >= lb.subset_capacity) {
+                    __syncwarp();
+                    const int lowest = __ffs(pending) - 1;
+                    bool first = mine;
+                    if (mine && j1 >= 0 && found <= 2) first = claim[j1] == lane && (found < 2 || claim[j2] == lane);
+                    if (mine && found > 2) first = lane == lowest;                   // IndexError: reported in order
+                    if (mine && ((scan_lanes >> lane) & 1u)) first = lane == lowest;
+                    // nobody may run ahead of a pending scan-path lane below it (its rows are unknown)
+                    const unsigned below_scan = scan_lanes & ((1u << lane) - 1);
+                    if (below_scan) first = false;
+                    __syncwarp();
+                    if (mine && j1 >= 0 && found <= 2) {                             // release the claims for the next round
+                        claim[j1] = 0x7fffffff;
+                        if (found == 2) claim[j2] = 0x7fffffff;
+                    }
+                    const unsigned run = __ballot_sync(0xffffffffu, first);
+                    // ---- simple cases in parallel
+                    const bool simple = first && !complex_case;
+                    const bool make_row = simple && found == 0 && k < 17;
+                    const unsigned newmask = __ballot_sync(0xffffffffu, make_row);
+                    if (nrows + __popc(newmask) > lb.subset_capacity) {
                         fail = true;
                         if (lane == 0) atomicOr(lb.status, ST_SUBSET_OVERFLOW);
                         break;
                     }
-                    if (lane < 18) rows[nrows * RS + lane] = lane == ia ? idA : (lane == ib ? idB : -1.0);
-                    if (lane == 18) rows[nrows * RS + 18] = ((0.0 + scoreA) + scoreB) + limb_score;
-                    if (lane == 19) rows[nrows * RS + 19] = 2.0;
-                    if (lane == 20) rows[nrows * RS + 20] = 0.0;
-                    if (lane == 0) {
-                        owner_add(own, a_id, nrows, own_overflow);
-                        if (b_id != a_id) owner_add(own, b_id, nrows, own_overflow);
+                    if (make_row) {
+                        const int r = nrows + __popc(newmask & ((1u << lane) - 1));
+                        const double idA = sconn[c][0];
+                        for (int q = 0; q < 18; ++q) rows[r * RS + q] = q == ia ? idA : (q == ib ? idB : -1.0);
+                        rows[r * RS + 18] = ((0.0 + sconn[c][3]) + sconn[c][4]) + sconn[c][2];
+                        rows[r * RS + 19] = 2.0;
+                        rows[r * RS + 20] = 0.0;
+                        owner_add(own, a_id, r, own_overflow);
+                        owner_add(own, b_id, r, own_overflow);
                     }
-                    ++nrows;
-                }
-                if (extend) {
-                    // found == 1 (src/body.py:176-181) and the overlapping found == 2 case (:189-193)
-                    if (lane == 0) {
-                        const double old = rows[j1 * RS + ib];
-                        if (found == 2 || old != idB) {
-                            if (old != idB) {
-                                if (old >= 0.0) owner_remove(own, (int)old, j1);      // overwritten, as in the reference
-                                owner_add(own, b_id, j1, own_overflow);
-                            }
-                            rows[j1 * RS + ib] = idB;
-                            rows[j1 * RS + 19] += 1.0;
-                            rows[j1 * RS + 18] += scoreB + limb_score;
-                        }
+                    nrows += __popc(newmask);
+                    if (simple && found == 1 && !noop) {
+                        rows[j1 * RS + ib] = idB;
+                        rows[j1 * RS + 19] += 1.0;
+                        rows[j1 * RS + 18] += sconn[c][4] + sconn[c][2];
+                        owner_add(own, b_id, j1, own_overflow);
                     }
+                    __syncwarp();
+                    // ---- the rest one connection at a time, in lane order, by the whole warp
+                    unsigned serial = __ballot_sync(0xffffffffu, first && complex_case);
+                    while (serial && !fail) {
+                        const int l = __ffs(serial) - 1;
+                        serial &= serial - 1;
+                        serial_one(g0 + l);
+                    }
+                    pending &= ~run;
                 }
-                __syncwarp();
             }
         }
     }
@@ -469,11 +561,11 @@ void paf_group_launch(const MapSource& paf, int n_frames, int H, int W, const Fr
     static bool attr[64] = {};
     if (first_use_on_device(attr)) {
         OPB_CUDA(cudaFuncSetAttribute(assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kSubsetRowsShared * kSubsetRowStride * 8 + 16 + kOwnerShared * 16));
+                                      kSubsetRowsShared * kSubsetRowStride * 8 + 16 + kOwnerShared * 16 + kSubsetRowsShared * 4));
     }
     // work rows (shared up to kSubsetRowsShared rows, else the frames' global buffers) + owner lists of the candidates
     const size_t rows_smem = (size_t)std::min(subset_capacity, kSubsetRowsShared) * kSubsetRowStride * 8 + 16;
-    assemble_kernel<<<n_frames, 32, rows_smem + kOwnerShared * 16, stream>>>(frames_dev);
+    assemble_kernel<<<n_frames, 32, rows_smem + kOwnerShared * 16 + kSubsetRowsShared * 4, stream>>>(frames_dev);
     OPB_CUDA(cudaGetLastError());
 }
 
