@@ -1719,12 +1719,20 @@ int opb_conv2d(opb_context* ctx, const void* dev_in, int n, int h, int w, int ci
         op.bias = dp.upload(bd);
         op.cout_pad = cout_pad; op.cout_store = cout_store; op.ks = k; op.relu = relu != 0; op.pool = pool != 0;
         // impl: 0 = the path the networks use, 1 = scalar cross-check, 2 = per-tap tiles, 3 / 4 = patch MODE 0 / 1,
-        // 5 = CTA-pair (cta_group::2) kernel
+        // 5 = CTA-pair (cta_group::2) kernel, 6 = the same in the wide-pixel pooled form
         int sel = impl;
         if (impl == 0) sel = (k > 1 && default_conv_impl() >= 0) ? 3 + default_conv_impl() : 2;
         if ((sel == 3 || sel == 4 || sel == 5) && k == 1) sel = 2;
         if (sel == 1) {
             conv_direct_launch(op, ctx->stream);
+        } else if (sel == 6) {                       // CTA-pair kernel, wide-pixel pooled form (the networks' conv1_2)
+            std::vector<__nv_bfloat16> ww;
+            std::vector<float> bw;
+            OPB_REQUIRE(cin == 64 && cout == 64 && k == 3, "opb_conv2d: impl 6 is the 64 -> 64 channel 3x3 + pool form");
+            wide_pool_weights(weight, bias, ww, bw);
+            const ConvOp wide = wide_pool_op(op, dp.upload(ww), dp.upload(bw));
+            std::unique_ptr<ConvLaunch> L(conv_pair_plan({wide}, 128, ctx->num_sms));
+            L->run(ctx->stream);
         } else if (sel == 2) {
             conv_tc_launch({op}, bn, ctx->stream, ctx->num_sms);
         } else {

@@ -21,12 +21,12 @@ namespace {
 
 using namespace tc;
 
-constexpr int kThreads = 224;
+constexpr int kThreads = 256;
 constexpr int kAccStages = 2;
 constexpr int kHalves = 2;
 constexpr int kTile = 16;
 constexpr int kPitch = 16;
-constexpr int FLAG_RELU = 1, FLAG_F32 = 2, FLAG_POOL = 4;
+constexpr int FLAG_RELU = 1, FLAG_F32 = 2, FLAG_POOL = 4, FLAG_POOLW = 8;
 
 struct QProb {
     void* out;
@@ -53,6 +53,12 @@ struct alignas(64) PairParams {
     int nprob, total_pairs, ks;
     int total_full;              // pairs [0, total_full) are full-cost, [total_full, total_pairs) half-cost: the round robin over
                                  // CTA pairs then gives every cluster the same share of each, and the last round is a cheap one
+    CUtensorMap tmWh;            // the weights of problem 0 with a box of a quarter N tile (half chunks; all problems share them)
+    unsigned khalf_lo, khalf_hi; // bit (chunk * ks + dx): only the lower / upper half of the N tile has non-zero weights there
+    int n_patch;                 // patch buffers in flight (4 for 3x3 layers, 3 for 7x7)
+    int bres;                    // > 0: one weight set of one N tile whose chunks all fit the weight stages (conv1_2 wide form, conv2_1):
+                                 // loaded once per CTA (bres bytes), never recycled
+    unsigned kskip;              // bit (chunk * ks + dx): that 64-channel chunk of column tap dx has all-zero weights (ConvOp::kskip)
     int resident;                // short-K layers (conv1_2: 3x3, 64 channels, one weight set): the 9 weight taps stay in shared
                                  // memory for the whole kernel and ONE 24-column patch per tile serves all three dx
 };
@@ -61,18 +67,20 @@ static_assert(sizeof(PairParams) <= 4000, "kernel parameter space");
 template <int BLOCK_N>
 struct QCfg {
     static constexpr int kPatchBytesMax = kPitch * (kTile + 6) * 128;      // 45056 (ks = 7)
-    static constexpr int kNumPatch = 3;
+    static constexpr int kNumPatch = 4;                                    // barriers; ks = 7 uses three buffers (n_patch below)
+    static constexpr int kPatchBytes3 = kPitch * (kTile + 2) * 128;        // 36864 (ks = 3): four of them
+    static constexpr int kPatchRegion = 4 * kPatchBytes3 > 3 * kPatchBytesMax ? 4 * kPatchBytes3 : 3 * kPatchBytesMax;
     static constexpr int kBHalfBytes = (BLOCK_N / 2) * 128;                 // this CTA's half of a weight stage
-    static constexpr int kBStages = BLOCK_N == 64 ? 9 : 8;     // 9: holds the 9 resident taps of a 3x3 layer (resident mode)
+    static constexpr int kBStages = 9;       // 9: room for every weight chunk of a short-K layer (bres / resident modes)
     static constexpr int kResPitch = 24;                                   // resident mode: patch columns (18 used)
     static constexpr int kResPatchBytes = kResPitch * (kTile + 2) * 128;   // 55296
-    static constexpr int kResPatchStride = (kNumPatch * kPatchBytesMax / 2) / 1024 * 1024;   // two buffers in the patch region
+    static constexpr int kResPatchStride = (kPatchRegion / 2) / 1024 * 1024;   // two buffers in the patch region
     static_assert(kResPatchBytes <= kResPatchStride, "resident patch buffers");
     static constexpr int kTmemCols = kAccStages * kHalves * BLOCK_N;
     static constexpr int kNumBars = 2 * kNumPatch + 2 * kBStages + 2 * kAccStages;
     static constexpr int kBarBytes = kNumBars * 8 + 16;
     static constexpr int kBiasBytes = kAccStages * BLOCK_N * 4;
-    static constexpr int kSmemBytes = 1024 + kNumPatch * kPatchBytesMax + kBStages * kBHalfBytes + kBarBytes + kBiasBytes;
+    static constexpr int kSmemBytes = 1024 + kPatchRegion + kBStages * kBHalfBytes + kBarBytes + kBiasBytes;
     static_assert(kBHalfBytes % 1024 == 0, "swizzle atoms must stay 1024-B aligned");
     static_assert(kSmemBytes <= 232448, "shared memory budget");
 };
@@ -86,6 +94,9 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
     d |= (uint64_t)2 << 61;
     return d;
 }
+
+// mask bit of K chunk `i` = channel chunk * ks + dx (layers with more than 32 chunks have no masks)
+__host__ __device__ __forceinline__ unsigned chunk_bit(int i) { return i < 32 ? 1u << i : 0u; }
 
 struct TileCoord {
     int pi, img, x0, y0, n0;
@@ -153,7 +164,7 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* patches = smem;
-    uint8_t* bstages = smem + C::kNumPatch * C::kPatchBytesMax;
+    uint8_t* bstages = smem + C::kPatchRegion;
     uint64_t* pfull = (uint64_t*)(bstages + C::kBStages * C::kBHalfBytes);
     uint64_t* pempty = pfull + C::kNumPatch;
     uint64_t* bfull = pempty + C::kNumPatch;
@@ -172,6 +183,9 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
     const int pad = ks >> 1;
     const int patch_rows = kTile + ks - 1;
     const uint32_t patch_bytes = (uint32_t)(kPitch * patch_rows * 128);
+    // a 3x3 patch feeds only 3 x 2 x 4 MMAs (~1500 clocks): four buffers in flight to cover the TMA latency; 7x7: three
+    const int n_patch = p.n_patch;
+    const uint32_t patch_stride = ks == 3 ? C::kPatchBytes3 : C::kPatchBytesMax;
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < p.nprob; ++i) {
@@ -180,14 +194,14 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
         }
         for (int s = 0; s < C::kNumPatch; ++s) {
             mbar_init(&pfull[s], 1);
-            mbar_init(&pempty[s], 1);
+            mbar_init(&pempty[s], kHalves);             // one commit per issuing warp
         }
         for (int s = 0; s < C::kBStages; ++s) {
             mbar_init(&bfull[s], 1);
-            mbar_init(&bempty[s], 1);
+            mbar_init(&bempty[s], kHalves);
         }
         for (int a = 0; a < kAccStages; ++a) {
-            mbar_init(&tfull[a], 1);
+            mbar_init(&tfull[a], kHalves);
             mbar_init(&tempty[a], 256);                 // 128 epilogue threads of each CTA (leader's copy is used)
         }
         fence_barrier_init();
@@ -226,11 +240,12 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 const CUtensorMap* tmA = &p.tmA[tc.pi];
                 for (int cc = 0; cc < cin_chunks; ++cc) {
                     for (int dx = 0; dx < ks; ++dx) {
+                        if (chunk_bit(cc * ks + dx) & p.kskip) continue;
                         mbar_wait(&pempty[pb], pphase ^ 1, 10);
                         if (rank == 0) mbar_arrive_expect_tx_elect(&pfull[pb], 2 * patch_bytes);
-                        tma_load_4d_2sm_elect(patches + pb * C::kPatchBytesMax, tmA, &pfull[pb], cc * 64, tc.x0 - pad + dx,
+                        tma_load_4d_2sm_elect(patches + pb * patch_stride, tmA, &pfull[pb], cc * 64, tc.x0 - pad + dx,
                                               tc.y0 - pad, tc.img);
-                        if (++pb == C::kNumPatch) { pb = 0; pphase ^= 1; }
+                        if (++pb == n_patch) { pb = 0; pphase ^= 1; }
                     }
                 }
             }
@@ -245,6 +260,25 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[t], 2 * C::kBHalfBytes);
                 tma_load_2d_2sm_elect(bstages + t * C::kBHalfBytes, &p.tmW[0], &bfull[t], t * 64, rank * (BLOCK_N / 2));
             }
+        } else if (p.bres) {
+            // every chunk once, in the order of the MMA walk, packed back to back; one barrier for the lot
+            const int cin_chunks = p.prob[0].cin_chunks;
+            if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[0], 2 * (uint32_t)p.bres);
+            uint32_t off = 0;
+            for (int cc = 0; cc < cin_chunks; ++cc)
+                for (int i = 0; i < ks * ks; ++i) {
+                    const int tap = (i % ks) * ks + (i / ks);
+                    const unsigned bit = chunk_bit(cc * ks + i / ks);
+                    if (p.kskip & bit) continue;
+                    if ((p.khalf_lo | p.khalf_hi) & bit) {
+                        tma_load_2d_2sm_elect(bstages + off, &p.tmWh, &bfull[0], (tap * cin_chunks + cc) * 64,
+                                              ((p.khalf_hi & bit) ? BLOCK_N / 2 : 0) + rank * (BLOCK_N / 4));
+                        off += C::kBHalfBytes / 2;
+                    } else {
+                        tma_load_2d_2sm_elect(bstages + off, &p.tmW[0], &bfull[0], (tap * cin_chunks + cc) * 64, rank * (BLOCK_N / 2));
+                        off += C::kBHalfBytes;
+                    }
+                }
         } else {
             for (int pr = cluster_id; pr < p.total_pairs; pr += n_clusters) {
                 const TileCoord tc = decode_pair(p, pr, rank, BLOCK_N);
@@ -253,19 +287,34 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 for (int cc = 0; cc < cin_chunks; ++cc) {
                     for (int i = 0; i < ks * ks; ++i) {
                         const int tap = (i % ks) * ks + (i / ks);              // dx outer, dy inner (matches the MMA walk)
+                        const unsigned bit = chunk_bit(cc * ks + i / ks);
+                        if (p.kskip & bit) continue;
                         mbar_wait(&bempty[bs], bphase ^ 1, 11);
-                        if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[bs], 2 * C::kBHalfBytes);
-                        tma_load_2d_2sm_elect(bstages + bs * C::kBHalfBytes, tmW, &bfull[bs], (tap * cin_chunks + cc) * 64,
-                                              tc.n0 + rank * (BLOCK_N / 2));
+                        if ((p.khalf_lo | p.khalf_hi) & bit) {
+                            // half chunk: N/2 weight rows in all, this CTA's quarter at the head of the stage
+                            if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[bs], C::kBHalfBytes);
+                            tma_load_2d_2sm_elect(bstages + bs * C::kBHalfBytes, &p.tmWh, &bfull[bs], (tap * cin_chunks + cc) * 64,
+                                                  tc.n0 + ((p.khalf_hi & bit) ? BLOCK_N / 2 : 0) + rank * (BLOCK_N / 4));
+                        } else {
+                            if (rank == 0) mbar_arrive_expect_tx_elect(&bfull[bs], 2 * C::kBHalfBytes);
+                            tma_load_2d_2sm_elect(bstages + bs * C::kBHalfBytes, tmW, &bfull[bs], (tap * cin_chunks + cc) * 64,
+                                                  tc.n0 + rank * (BLOCK_N / 2));
+                        }
                         if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 1) {
-        // ================= MMA issuer (leader CTA only) =================
+    } else if (warp == 1 || warp == 7) {
+        // ================= MMA issuers (leader CTA only) =================
+        // Two warps, one per 128-pixel half of the super-tiles (each half has its own accumulator columns, so the two MMA
+        // streams are independent): one thread could not keep up with short-K layers -- ncu on conv1_2 showed the issuing
+        // warp never waiting on a barrier while the tensor pipe idled 45 % of the time.  Each warp waits for the same
+        // operands and commits its own MMAs, so the empty / accumulator-full barriers count two arrivals.
+        const int h = warp == 1 ? 0 : 1;
         if (rank == 0) {
             constexpr uint32_t idesc = make_idesc_2sm(BLOCK_N);
+            constexpr uint32_t idesc_half = make_idesc_2sm(BLOCK_N / 2);
             int pb = 0, bs = 0, acc = 0;
             uint32_t pphase = 0, bphase = 0, acc_phase = 0;
             bool first_tile = true;
@@ -276,7 +325,8 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 const int halves = tc.halves | decode_pair(p, pr, 1, BLOCK_N).halves;
                 const uint32_t half_off = q.vsplit ? 8u * kPitch * 128u : 8u * 128u;
                 const uint32_t sbo = q.vsplit ? 1024u : (uint32_t)(kPitch * 128);
-                uint32_t accum[kHalves] = {0, 0};
+                uint32_t accum = 0;
+                const bool mine = halves & (1 << h);
                 mbar_wait(&tempty[acc], acc_phase ^ 1, 12);               // both epilogues drained this accumulator
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * (kHalves * BLOCK_N);
@@ -294,15 +344,13 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                         }
                         const int dy = t / ks, dx = t - dy * ks;
                         const uint64_t bdesc = make_desc(smem_u32(bstages + t * C::kBHalfBytes), 1024);
-#pragma unroll
-                        for (int h = 0; h < kHalves; ++h) {
-                            if (!(halves & (1 << h))) continue;
+                        if (mine) {
                             const uint64_t adesc = make_desc(patch_addr + (uint32_t)((dy * C::kResPitch + dx + h * 8) * 128),
                                                              C::kResPitch * 128);
 #pragma unroll
                             for (int k = 0; k < 4; ++k) {
-                                umma_bf16_2sm_elect(d_tmem + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, accum[h]);
-                                accum[h] = 1;
+                                umma_bf16_2sm_elect(d_tmem + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, accum);
+                                accum = 1;
                             }
                         }
                     }
@@ -310,32 +358,52 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                     umma_commit_2sm_elect(&pempty[pb]);
                     pb ^= 1;
                     if (pb == 0) pphase ^= 1;
-                } else
+                } else {
+                uint32_t boff = 0;                                        // bres: where this chunk's weights sit
                 for (int cc = 0; cc < q.cin_chunks; ++cc) {
                     for (int sh = 0; sh < ks; ++sh) {
+                        const unsigned bit = chunk_bit(cc * ks + sh);
+                        if (p.kskip & bit) continue;
+                        const bool half_n = (p.khalf_lo | p.khalf_hi) & bit;
+                        const uint32_t idesc_use = half_n ? idesc_half : idesc;
+                        const uint32_t dcol = (p.khalf_hi & bit) ? BLOCK_N / 2 : 0;
                         mbar_wait(&pfull[pb], pphase, 13);                // both CTAs' patches have landed
                         tc_fence_after();
-                        const uint32_t patch_addr = smem_u32(patches + pb * C::kPatchBytesMax);
+                        const uint32_t patch_addr = smem_u32(patches + pb * patch_stride);
                         for (int dy = 0; dy < ks; ++dy) {
-                            mbar_wait(&bfull[bs], bphase, 14);            // both weight halves have landed
-                            tc_fence_after();
-                            const uint64_t bdesc = make_desc(smem_u32(bstages + bs * C::kBHalfBytes), 1024);
-#pragma unroll
-                            for (int h = 0; h < kHalves; ++h) {
-                                if (!(halves & (1 << h))) continue;
+                            uint32_t baddr;
+                            if (p.bres) {
+                                if (first_tile) {
+                                    mbar_wait(&bfull[0], 0, 14);          // the whole weight set has landed in both CTAs
+                                    tc_fence_after();
+                                    first_tile = false;
+                                }
+                                baddr = smem_u32(bstages) + boff;
+                                boff += half_n ? C::kBHalfBytes / 2 : C::kBHalfBytes;
+                            } else {
+                                mbar_wait(&bfull[bs], bphase, 14);        // both weight halves have landed
+                                tc_fence_after();
+                                baddr = smem_u32(bstages + bs * C::kBHalfBytes);
+                            }
+                            const uint64_t bdesc = make_desc(baddr, 1024);
+                            if (mine) {
                                 const uint64_t adesc = make_desc(patch_addr + (uint32_t)(dy * kPitch * 128) + h * half_off, sbo);
 #pragma unroll
                                 for (int k = 0; k < 4; ++k) {
-                                    umma_bf16_2sm_elect(d_tmem + h * BLOCK_N, adesc + 2 * k, bdesc + 2 * k, idesc, accum[h]);
-                                    accum[h] = 1;
+                                    // (a half chunk is never the first of a tile: conv_pair_plan checks)
+                                    umma_bf16_2sm_elect(d_tmem + h * BLOCK_N + dcol, adesc + 2 * k, bdesc + 2 * k, idesc_use, accum);
+                                    accum = 1;
                                 }
                             }
-                            umma_commit_2sm_elect(&bempty[bs]);
-                            if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+                            if (!p.bres) {
+                                umma_commit_2sm_elect(&bempty[bs]);
+                                if (++bs == C::kBStages) { bs = 0; bphase ^= 1; }
+                            }
                         }
                         umma_commit_2sm_elect(&pempty[pb]);
-                        if (++pb == C::kNumPatch) { pb = 0; pphase ^= 1; }
+                        if (++pb == n_patch) { pb = 0; pphase ^= 1; }
                     }
+                }
                 }
                 umma_commit_2sm_elect(&tfull[acc]);
                 if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
@@ -367,6 +435,7 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
             const bool relu = q.flags & FLAG_RELU;
             const bool pool = q.flags & FLAG_POOL;
             const bool f32 = q.flags & FLAG_F32;
+            const bool poolw = q.flags & FLAG_POOLW;
             const int n_valid = q.cout_store - tc.n0;
             const bool vsplit = q.vsplit != 0;
             // pixel of accumulator row `row` inside the half: 8 x 16 (side by side) or 16 x 8 (stacked)
@@ -384,7 +453,10 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 const bool inside = (x < q.W) && (y < q.H);
                 size_t pix;
                 bool writer;
-                if (pool) {
+                if (poolw) {
+                    pix = ((size_t)tc.img * (q.H >> 1) + (y >> 1)) * q.W + x;
+                    writer = inside && !(ty & 1);
+                } else if (pool) {
                     pix = ((size_t)tc.img * (q.H >> 1) + (y >> 1)) * (q.W >> 1) + (x >> 1);
                     writer = inside && !(tx & 1) && !(ty & 1);
                 } else {
@@ -393,6 +465,25 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 }
                 const size_t out_off = pix * q.out_cstride + tc.n0;
                 const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (kHalves * BLOCK_N) + h * BLOCK_N;
+                if (poolw) {
+                    // wide pixel: columns c and 64 + c are channel c of the even and of the odd image column
+#pragma unroll 1
+                    for (int c0 = 0; c0 < 64; c0 += 32) {
+                        uint32_t v0[32], v1[32];
+                        tmem_ld32(taddr + c0, v0);
+                        tmem_ld32(taddr + 64 + c0, v1);
+                        float f[32];
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float a = fmaxf(__uint_as_float(v0[j]) + bias_s[c0 + j], 0.f);
+                            const float b = fmaxf(__uint_as_float(v1[j]) + bias_s[64 + c0 + j], 0.f);
+                            const float m = fmaxf(a, b);
+                            f[j] = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, pool_dy));
+                        }
+                        if (writer) store_bf16x32((__nv_bfloat16*)q.out + out_off + c0, f, 64 - c0);
+                    }
+                    continue;
+                }
 #pragma unroll 1
                 for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
                     if (c0 >= n_valid) break;
@@ -474,6 +565,27 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
     memset(&P, 0, sizeof(P));
     P.nprob = (int)ops.size();
     P.ks = ops[0].ks;
+    P.kskip = ops[0].kskip;
+    {
+        static const char* np = getenv("OPB_PAIR_PATCHES");
+        P.n_patch = P.ks == 3 ? 4 : 3;
+        if (np && atoi(np) >= 2 && atoi(np) <= P.n_patch) P.n_patch = atoi(np);
+    }
+    P.khalf_lo = ops[0].khalf_lo;
+    P.khalf_hi = ops[0].khalf_hi;
+    if (P.khalf_lo | P.khalf_hi) {
+        OPB_REQUIRE(block_n == 128 && !(P.khalf_lo & P.khalf_hi) && !((P.khalf_lo | P.khalf_hi) & P.kskip),
+                    "conv_pair: half chunks need the 128-wide N tile and disjoint masks");
+        int first = 0;
+        while ((P.kskip >> first) & 1) ++first;
+        OPB_REQUIRE(!(((P.khalf_lo | P.khalf_hi) >> first) & 1), "conv_pair: the first chunk of a tile must span the whole N tile");
+        const ConvOp& op = ops[0];
+        const cuuint64_t K = (cuuint64_t)op.ks * op.ks * op.in.c;
+        cuuint64_t wdims[2] = {K, (cuuint64_t)op.cout_pad};
+        cuuint64_t wstr[1] = {K * 2};
+        cuuint32_t wbox[2] = {64, (cuuint32_t)(block_n / 4)};
+        tensor_map_encode_bf16(&P.tmWh, (void*)op.w, 2, wdims, wstr, wbox);
+    }
     OPB_REQUIRE(P.ks == 3 || P.ks == 7, "conv_pair: kernel size 3 or 7");
     // Small launches (a 640x480 frame at scale 0.5 gives 4 super-tiles per stage layer): when full 16x16 super-tiles
     // would occupy at most a quarter of the CTA pairs the GPU holds, every CTA takes one 16x8 half instead -- twice the
@@ -483,7 +595,7 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         long full_pairs = 0;
         for (const ConvOp& op : ops) {
             full_pairs += (long)((cdiv(op.in.w, kTile) * cdiv(op.in.h, kTile) * op.in.n + 1) / 2) * (op.cout_pad / block_n);
-            if (op.pool) small = false;
+            if (op.pool || op.pool_wide) small = false;
         }
         if (full_pairs * 4 > num_sms / 2) small = false;
     }
@@ -507,7 +619,15 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         OPB_REQUIRE((op.out.coff * op.out.elem) % 16 == 0 && (op.out.cstride * op.out.elem) % 16 == 0,
                     "conv_pair: output slice must be 16-byte aligned");
         const int H = op.in.h, W = op.in.w, N = op.in.n;
-        if (op.pool) {
+        OPB_REQUIRE(op.kskip == ops[0].kskip && op.khalf_lo == ops[0].khalf_lo && op.khalf_hi == ops[0].khalf_hi &&
+                        ((op.khalf_lo | op.khalf_hi) == 0 || op.w == ops[0].w),
+                    "conv_pair: grouped problems must share the zero-chunk masks (and the weights when there are half chunks)");
+        if (op.pool_wide) {
+            OPB_REQUIRE(block_n == 128 && op.cout_pad == 128 && op.in.c == 128 && P.ks == 3 && op.relu && !op.pool && H % 2 == 0 &&
+                            op.out.elem == 2,
+                        "conv_pair: wide-pixel pooled form is 128 -> 128 columns, 3x3, ReLU, even rows, bf16 out");
+            OPB_REQUIRE(op.out.h == H / 2 && op.out.w == W && op.out.n == N && op.out.c == 64, "conv_pair: wide-pixel output dims");
+        } else if (op.pool) {
             OPB_REQUIRE(H % 2 == 0 && W % 2 == 0 && op.relu, "conv_pair: fused pool needs even dims and ReLU");
             OPB_REQUIRE(op.out.h == H / 2 && op.out.w == W / 2 && op.out.n == N, "conv_pair: pooled output dims");
         } else {
@@ -526,7 +646,8 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         q.cout_store = op.cout_store;
         q.n_tiles_n = op.cout_pad / block_n;
         q.cin_chunks = op.in.c / 64;
-        q.flags = (op.relu ? FLAG_RELU : 0) | (op.out.elem == 4 ? FLAG_F32 : 0) | (op.pool ? FLAG_POOL : 0);
+        q.flags = (op.relu ? FLAG_RELU : 0) | (op.out.elem == 4 ? FLAG_F32 : 0) | (op.pool ? FLAG_POOL : 0) |
+                  (op.pool_wide ? FLAG_POOLW : 0);
         {
             // 128-pixel halves actually multiplied: side by side -> columns round up to 8 and rows to 16; stacked ->
             // columns to 16 and rows to 8 (e.g. 41x23: 48x32 vs 48x24; 82x46: 88x48 vs 96x48)
@@ -553,6 +674,19 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         cuuint64_t wstr[1] = {K * 2};
         cuuint32_t wbox[2] = {64, (cuuint32_t)(block_n / 2)};
         tensor_map_encode_bf16(&P.tmW[i], (void*)op.w, 2, wdims, wstr, wbox);
+    }
+    // weights resident for the whole kernel: one weight set, one N tile, and every chunk fits the weight stages
+    if (!resident && getenv("OPB_NO_BRES") == nullptr) {
+        bool same = true;
+        for (const ConvOp& op : ops) same = same && op.w == ops[0].w && op.cout_pad == block_n && op.in.c == ops[0].in.c;
+        long bytes = 0;
+        for (int cc = 0; cc < ops[0].in.c / 64; ++cc)
+            for (int dx = 0; dx < P.ks; ++dx) {
+                const unsigned bit = chunk_bit(cc * P.ks + dx);
+                if (P.kskip & bit) continue;
+                bytes += (long)P.ks * (((P.khalf_lo | P.khalf_hi) & bit) ? (block_n / 4) * 128 : (block_n / 2) * 128);
+            }
+        if (same && bytes <= (long)9 * (block_n / 2) * 128) P.bres = (int)bytes;
     }
     // launch order: the full-cost pairs of every problem, then the half-cost pairs of every problem
     {

@@ -141,6 +141,58 @@ static std::vector<int> input_channel_map(int kind, const LayerSpec& s) {
 
 static float bf16_round(float f) { return __bfloat162float(__float2bfloat16_rn(f)); }
 
+// A 3x3 layer on 64 channels gives a 64-wide N tile, and a tcgen05 MMA of N = 64 spends as long fetching its A operand
+// from shared memory as one of N = 128 while doing half the arithmetic (conv1_2 ran at 0.48 of the rate of the N = 128
+// layers).  Pairing horizontally adjacent pixels turns the layer into a 128 -> 128 channel one on an image of half the
+// width: input "channel" (parity pi, c) of wide pixel i is channel c of column 2 i + pi, output column (po, co) is channel
+// co of column 2 i + po, and the weight of wide tap (dy, di) is the original tap dx = 2 di + pi - po where that is in
+// [-1, 1] and zero elsewhere.  Of the 6 (di, pi) chunks of 64 input channels per dy, (di = -1, pi = 0) and (di = +1, pi = 1)
+// are entirely zero and are skipped (kskip); (di = -1, pi = 1) feeds the even output column only and (di = +1, pi = 0) the
+// odd one only, and run as MMAs of N = 64 into that half of the accumulator (khalf_lo / khalf_hi).  Per dy that leaves
+// two MMAs of N = 128 and two of N = 64 for three taps of useful work (6 N=64-equivalents issued for 6 useful).
+// The arithmetic per output element is unchanged: the same nine 64-term dot products accumulate in fp32 in the same
+// chunk order (dx outer, dy inner), zero weights add exact zeros.
+void wide_pool_weights(const float* weight, const float* bias, std::vector<__nv_bfloat16>& w_wide, std::vector<float>& b_wide) {
+    const size_t K = 9 * 128;
+    w_wide.assign(128 * K, __float2bfloat16_rn(0.f));
+    b_wide.assign(128, 0.f);
+    for (int po = 0; po < 2; ++po)
+        for (int co = 0; co < 64; ++co) {
+            b_wide[po * 64 + co] = bias[co];
+            for (int dy = 0; dy < 3; ++dy)
+                for (int di = 0; di < 3; ++di)
+                    for (int pi = 0; pi < 2; ++pi) {
+                        const int dx = 2 * (di - 1) + pi - po;           // signed original column tap
+                        if (dx < -1 || dx > 1) continue;
+                        const int t = dy * 3 + dx + 1;
+                        for (int c = 0; c < 64; ++c)
+                            w_wide[(size_t)(po * 64 + co) * K + (size_t)(dy * 3 + di) * 128 + pi * 64 + c] =
+                                __float2bfloat16_rn(weight[((size_t)co * 64 + c) * 9 + t]);
+                    }
+        }
+}
+bool wide_pool_ok(const ConvOp& b) {
+    return b.ks == 3 && b.pool && b.relu && b.in.c == 64 && b.in.cstride == 64 && b.in.coff == 0 && b.in.elem == 2 &&
+           b.in.w % 2 == 0 && b.in.h % 2 == 0 && b.out.elem == 2 && b.out.c == 64 && b.out.cstride == 64 && b.out.coff == 0;
+}
+ConvOp wide_pool_op(const ConvOp& base, const __nv_bfloat16* w_wide, const float* b_wide) {
+    OPB_REQUIRE(wide_pool_ok(base), "wide_pool_op: 64 -> 64 channel 3x3 + pool on contiguous bf16 tensors of even size");
+    ConvOp op = base;
+    op.in.w = base.in.w / 2;
+    op.in.c = op.in.cstride = 128;
+    op.w = w_wide;
+    op.bias = b_wide;
+    op.cout_pad = op.cout_store = 128;
+    op.pool = false;
+    op.pool_wide = true;
+    op.kskip = (1u << (0 * 3 + 0)) | (1u << (1 * 3 + 2));     // (pi 0, di -1) and (pi 1, di +1)
+    if (getenv("OPB_WIDE_FULL_N") == nullptr) {
+        op.khalf_lo = 1u << (1 * 3 + 0);                      // (pi 1, di -1) feeds the even output column only
+        op.khalf_hi = 1u << (0 * 3 + 2);                      // (pi 0, di +1) the odd one only
+    }
+    return op;
+}
+
 void finalize_net(opb_net* net) {
     const auto& specs = layer_specs(net->kind);
     for (const auto& s : specs) {
@@ -199,6 +251,15 @@ void finalize_net(opb_net* net) {
             for (int co = 0; co < s.cout; ++co) b[co] = h.b[co];
             d.bias = (float*)dalloc(b.size() * 4);
             OPB_CUDA(cudaMemcpy(d.bias, b.data(), b.size() * 4, cudaMemcpyHostToDevice));
+            if (s.k == 3 && s.cin == 64 && s.cout == 64 && s.pool_after) {
+                std::vector<__nv_bfloat16> ww;
+                std::vector<float> bw;
+                wide_pool_weights(h.w.data(), h.b.data(), ww, bw);
+                d.w_wide = (__nv_bfloat16*)dalloc(ww.size() * 2);
+                OPB_CUDA(cudaMemcpy(d.w_wide, ww.data(), ww.size() * 2, cudaMemcpyHostToDevice));
+                d.bias_wide = (float*)dalloc(bw.size() * 4);
+                OPB_CUDA(cudaMemcpy(d.bias_wide, bw.data(), bw.size() * 4, cudaMemcpyHostToDevice));
+            }
         }
         net->dev[s.name] = d;
     }
@@ -259,6 +320,19 @@ struct Builder {
             // their latency is the depth of one tile's K loop: halve the N tile so that twice as many CTA pairs share
             // the work and every UMMA is half as long.
             int bn_run = bn;
+            // conv1_2: wide-pixel form (wide_pool_weights above); OPB_NO_WIDE_CONV12=1 keeps the N = 64 launch
+            if (conv_impl == 2 && pool && getenv("OPB_NO_WIDE_CONV12") == nullptr) {
+                bool wide = true;
+                for (size_t j = 0; j < ops.size(); ++j)
+                    wide = wide && net->dev.at(names[first + j]).w_wide != nullptr && wide_pool_ok(ops[j]);
+                if (wide) {
+                    for (size_t j = 0; j < ops.size(); ++j) {
+                        const DevLayer& d = net->dev.at(names[first + j]);
+                        ops[j] = wide_pool_op(ops[j], d.w_wide, d.bias_wide);
+                    }
+                    bn_run = 128;
+                }
+            }
             if (ops[0].ks > 1 && conv_impl == 2 && bn == 128 && getenv("OPB_NO_SMALL_BN") == nullptr) {
                 long clusters = 0;
                 for (const ConvOp& op : ops)

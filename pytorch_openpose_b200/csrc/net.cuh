@@ -19,6 +19,8 @@ struct DevLayer {
     __nv_bfloat16* w = nullptr;   // [cout_pad][k*k*cin_dev] bf16 (tensor-core layers)
     float* w_first = nullptr;     // [27][64] fp32 holding bf16-rounded values (conv1_1 only)
     float* bias = nullptr;        // [cout_pad] fp32
+    __nv_bfloat16* w_wide = nullptr;   // 64 -> 64 channel 3x3 layers (conv1_2): [128][9 * 128] wide-pixel weights (wide_pool_weights)
+    float* bias_wide = nullptr;        // [128]: the bias twice
     int cin_dev = 0;              // channels of the device input view (padded / permuted)
     int cout_pad = 0, cout_store = 0, block_n = 128, k = 3;
     bool relu = true;
@@ -132,6 +134,11 @@ std::unique_ptr<NetPlan> build_net_plan(opb_net* net, const std::vector<NetShape
 void finalize_net(opb_net* net);
 constexpr int kDefaultConvImpl = 2;       // measured on B200 (bench.py, 720p 4-scale, same box): CTA pair 3.60 ms of conv per frame, patch MODE 1 3.79, MODE 0 and per-tap slower
 int default_conv_impl();
+// Wide-pixel form of a 64 -> 64 channel 3x3 layer + 2x2 pool (ConvOp::pool_wide).  weight: [64][64][9] fp32 (cout, cin, tap).
+void wide_pool_weights(const float* weight, const float* bias, std::vector<__nv_bfloat16>& w_wide, std::vector<float>& b_wide);
+// `base`: the layer as a plain pooled problem (in (n, h, w, 64) contiguous, out (n, h/2, w/2, 64)); w even.
+ConvOp wide_pool_op(const ConvOp& base, const __nv_bfloat16* w_wide, const float* b_wide);
+bool wide_pool_ok(const ConvOp& base);
 
 // cubic tap tables (host)
 struct CubicTaps {

@@ -65,6 +65,14 @@ struct ConvOp {                 // one problem of a grouped launch
     int ks = 3;                 // 1, 3 or 7 (stride 1, same padding)
     bool relu = true;
     bool pool = false;          // fused 2x2/2 max-pool of the ReLU output
+    // "wide pixel" form of a 64 -> 64 channel 3x3 layer followed by the pool (conv1_2; net.cu wide_pool_op): `in` views the
+    // image as (h, w/2) pixels of 128 channels (column parity x 64), the 128 output columns are the 64 channels of the even
+    // and of the odd column, and the pool is a max over the two column halves and over row pairs.  `kskip` bit
+    // (chunk * ks + dx) marks the 64-channel K chunks of a column tap whose weights are all zero: never loaded, never multiplied.
+    // `khalf_lo` / `khalf_hi` (same bit index): chunks whose weights are zero for the upper / lower half of the N tile --
+    // multiplied as an MMA of half the N extent into that half of the accumulator columns only.
+    bool pool_wide = false;
+    unsigned kskip = 0, khalf_lo = 0, khalf_hi = 0;
 };
 
 void conv_tc_launch(const std::vector<ConvOp>& ops, int block_n, cudaStream_t stream, int num_sms);

@@ -84,6 +84,27 @@ def test_conv_pair_resident_variant(case, monkeypatch):
     assert (out[..., :cout] - ref).abs().max().item() <= 2e-3 * scale + scale * 2 ** -8
 
 
+@pytest.mark.parametrize("shape", [(1, 24, 40), (2, 50, 70), (1, 184, 328), (3, 16, 18), (1, 2, 2), (1, 38, 250)],
+                         ids=lambda s: "n%d_%dx%d" % s)
+def test_conv_pair_wide_pixel_form(shape):
+    """conv1_2 as the networks run it: pairs of adjacent columns as one 128-channel pixel, 128 output columns, all-zero
+    weight chunks skipped, pool over the column halves and row pairs (net.cu wide_pool_weights) -- same contract; against
+    the plain N = 64 launch of the same layer only the fp32 accumulation order of the nine taps differs (one bf16 ulp)."""
+    from tests import gpu_util as G
+    n, h, w = shape
+    g = torch.Generator().manual_seed(1000 + h * w)
+    x = (torch.randn(n, h, w, 64, generator=g) * 0.5).to(torch.bfloat16).cuda()
+    wt = torch.randn(64, 64, 3, 3, generator=g) * (2.0 / (64 * 9)) ** 0.5
+    b = torch.randn(64, generator=g) * 0.1
+    ref = _reference(x, wt, b, True, True)
+    out = G.conv2d(x, wt, b, True, True, False, impl=6).float()
+    plain = G.conv2d(x, wt, b, True, True, False, impl=5).float()
+    assert out.shape == ref.shape and not torch.isnan(out).any()
+    scale = ref.abs().max().item()
+    assert (out - ref).abs().max().item() <= 2e-3 * scale + scale * 2 ** -8
+    assert (out - plain).abs().max().item() <= scale * 2 ** -8
+
+
 def test_conv_direct_crosscheck():
     """The scalar cross-check kernel obeys the same contract (used to bisect tensor-core issues)."""
     from tests import gpu_util as G
