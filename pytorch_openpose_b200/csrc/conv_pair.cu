@@ -40,10 +40,16 @@ struct QProb {
     int edge_begin;              // first index of its half-cost pairs (both tiles have an empty half), after ALL full-cost pairs
     int n_full_pairs;            // pairs of the problem whose first tile has two occupied halves (x n_tiles_n in the order)
     int tile_h;                  // 16, or 8 for small problems: one 16 x 8 half per CTA, twice the CTA pairs, half the K-loop depth
-    int n_full_img;              // super-tiles per image whose two halves both hold pixels (they come first in the tile order)
     int noskip;                  // A/B switch: multiply empty halves too
-    int vsplit;                  // 0: the two 128-pixel halves of a super-tile sit side by side (8 cols x 16 rows each),
-                                 // 1: stacked (16 cols x 8 rows each) -- chosen per problem for the least padding
+    int vsplit;                  // orientation of the tiles with two occupied halves: 0 = the two 128-pixel halves sit side by
+                                 // side (8 cols x 16 rows each), 1 = stacked (16 cols x 8 rows each)
+    // Tile classes (in this order in the problem's tile list, each padded to an even count so that the two tiles of a CTA
+    // pair always share class and orientation):  F = both halves hold pixels (fx x fy tiles per image);  C = last tile
+    // column when at most 8 image columns remain there: side by side, left half only (fy per image);  R = last tile row
+    // when at most 8 rows remain: stacked, top half only (tiles_x per image, corner included).
+    int fx, fy;
+    int nF, nC, nR;              // real tiles per class over all images
+    int startC, startR;          // first tile index of class C / R (even)
 };
 
 struct alignas(64) PairParams {
@@ -102,6 +108,7 @@ struct TileCoord {
     int pi, img, x0, y0, n0;
     bool real;                   // false: padding tile of an odd problem (computed, never stored)
     int halves;                  // bit h: half h of the super-tile holds at least one pixel of the image
+    int vsplit;                  // orientation of this tile (QProb::vsplit for class F, 0 for C, 1 for R)
 };
 __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, int rank, int block_n) {
     int pi = 0, local;
@@ -115,45 +122,45 @@ __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, in
     const QProb& q = p.prob[pi];
     const int nt = local % q.n_tiles_n;
     const int mp = local / q.n_tiles_n;
-    int mt = 2 * mp + rank;
+    const int mt = 2 * mp + rank;
     TileCoord c;
-    c.real = mt < q.m_tiles;
-    if (!c.real) mt = q.m_tiles - 1;
-    // Tile order of a problem: first every super-tile with two occupied halves (all images), then the edge tiles whose
-    // second half lies outside the image (last tile row when the halves are stacked, last tile column when they sit
-    // side by side) -- so the two tiles of a pair agree on which halves to skip, except for at most one pair.
-    const int per_img = q.tiles_x * q.tiles_y;
-    const int n_edge_img = per_img - q.n_full_img;
-    int img, txi, tyi;
-    if (mt < q.N * q.n_full_img) {
-        img = mt / q.n_full_img;
-        const int r = mt - img * q.n_full_img;
-        if (q.vsplit) {
-            tyi = r / q.tiles_x;
-            txi = r - tyi * q.tiles_x;
-        } else {
-            txi = r / q.tiles_y;
-            tyi = r - txi * q.tiles_y;
-        }
-    } else {
-        const int e = mt - q.N * q.n_full_img;
-        img = e / n_edge_img;
-        const int i = e - img * n_edge_img;
-        if (q.vsplit) {
-            txi = i;
-            tyi = q.tiles_y - 1;
-        } else {
-            txi = q.tiles_x - 1;
-            tyi = i;
-        }
+    int img, txi, tyi, idx;
+    if (mt < q.startC) {                                  // class F, row-major inside an image
+        idx = mt;
+        c.real = idx < q.nF;
+        if (!c.real) idx = q.nF - 1;
+        const int per = q.fx * q.fy;
+        img = idx / per;
+        const int r = idx - img * per;
+        tyi = r / q.fx;
+        txi = r - tyi * q.fx;
+        c.vsplit = q.vsplit;
+        c.halves = (q.tile_h == kTile) ? 3 : 1;
+    } else if (mt < q.startR) {                           // class C
+        idx = mt - q.startC;
+        c.real = idx < q.nC;
+        if (!c.real) idx = q.nC - 1;
+        img = idx / q.fy;
+        tyi = idx - img * q.fy;
+        txi = q.tiles_x - 1;
+        c.vsplit = 0;
+        c.halves = 1;
+    } else {                                              // class R
+        idx = mt - q.startR;
+        c.real = idx < q.nR;
+        if (!c.real) idx = q.nR - 1;
+        img = idx / q.tiles_x;
+        txi = idx - img * q.tiles_x;
+        tyi = q.tiles_y - 1;
+        c.vsplit = 1;
+        c.halves = 1;
     }
     c.pi = pi;
     c.img = img;
     c.x0 = txi * kTile;
     c.y0 = tyi * q.tile_h;
     c.n0 = nt * block_n;
-    const bool second = q.tile_h == kTile && (q.noskip || (q.vsplit ? (c.y0 + 8 < q.H) : (c.x0 + 8 < q.W)));
-    c.halves = c.real ? (second ? 3 : 1) : 0;
+    if (!c.real) c.halves = 0;
     return c;
 }
 
@@ -323,8 +330,8 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
                 const QProb& q = p.prob[tc.pi];
                 // a half that is outside the image in BOTH tiles of the pair is neither multiplied nor stored
                 const int halves = tc.halves | decode_pair(p, pr, 1, BLOCK_N).halves;
-                const uint32_t half_off = q.vsplit ? 8u * kPitch * 128u : 8u * 128u;
-                const uint32_t sbo = q.vsplit ? 1024u : (uint32_t)(kPitch * 128);
+                const uint32_t half_off = tc.vsplit ? 8u * kPitch * 128u : 8u * 128u;
+                const uint32_t sbo = tc.vsplit ? 1024u : (uint32_t)(kPitch * 128);
                 uint32_t accum = 0;
                 const bool mine = halves & (1 << h);
                 mbar_wait(&tempty[acc], acc_phase ^ 1, 12);               // both epilogues drained this accumulator
@@ -437,7 +444,7 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
             const bool f32 = q.flags & FLAG_F32;
             const bool poolw = q.flags & FLAG_POOLW;
             const int n_valid = q.cout_store - tc.n0;
-            const bool vsplit = q.vsplit != 0;
+            const bool vsplit = tc.vsplit != 0;
             // pixel of accumulator row `row` inside the half: 8 x 16 (side by side) or 16 x 8 (stacked)
             const int tx = vsplit ? (row & 15) : (row & 7);
             const int ty = vsplit ? (row >> 4) : (row >> 3);
@@ -640,8 +647,6 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         q.tile_h = small ? 8 : kTile;
         q.tiles_x = cdiv(W, kTile);
         q.tiles_y = cdiv(H, q.tile_h);
-        q.m_tiles = q.tiles_x * q.tiles_y * N;
-        q.m_pairs = (q.m_tiles + 1) / 2;
         q.out_cstride = op.out.cstride;
         q.cout_store = op.cout_store;
         q.n_tiles_n = op.cout_pad / block_n;
@@ -649,19 +654,32 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         q.flags = (op.relu ? FLAG_RELU : 0) | (op.out.elem == 4 ? FLAG_F32 : 0) | (op.pool ? FLAG_POOL : 0) |
                   (op.pool_wide ? FLAG_POOLW : 0);
         {
-            // 128-pixel halves actually multiplied: side by side -> columns round up to 8 and rows to 16; stacked ->
-            // columns to 16 and rows to 8 (e.g. 41x23: 48x32 vs 48x24; 82x46: 88x48 vs 96x48)
+            // 128-pixel halves actually multiplied.  A tile with pixels in both halves costs 256 rows whatever its
+            // orientation; the last tile column is split side by side when at most 8 columns remain there, the last tile
+            // row stacked when at most 8 rows remain, and their empty half is skipped: columns and rows both round up to 8
+            // (41x23: 48x24, 82x46: 88x48, 69x69: 72x72, 23x23: 24x24).  OPB_PAIR_NO_MIXED=1: one orientation per problem
+            // (the one with the least padding), i.e. only one of the two edges profits.
             static const char* force = getenv("OPB_PAIR_SPLIT");
             static const char* noskip = getenv("OPB_PAIR_NOSKIP");
+            static const bool mixed = getenv("OPB_PAIR_NO_MIXED") == nullptr;
             const long side = (long)cdiv(W, 8) * 8 * cdiv(H, 16) * 16, stacked = (long)cdiv(W, 16) * 16 * cdiv(H, 8) * 8;
             q.vsplit = small ? 1 : (resident ? 0 : (force ? atoi(force) : (stacked < side ? 1 : 0)));   // 24-column patches: side by side only
             q.noskip = noskip ? 1 : 0;
-            const bool edge = !small && !q.noskip &&
-                              (q.vsplit ? ((q.tiles_y - 1) * kTile + 8 >= H) : ((q.tiles_x - 1) * kTile + 8 >= W));
-            q.n_full_img = q.tiles_x * q.tiles_y - (edge ? (q.vsplit ? q.tiles_x : q.tiles_y) : 0);
+            const bool skip = !small && !q.noskip;
+            const bool has_c = skip && (q.tiles_x - 1) * kTile + 8 >= W && (mixed || q.vsplit == 0);
+            const bool has_r = skip && (q.tiles_y - 1) * kTile + 8 >= H && !resident && (mixed || q.vsplit == 1);
+            q.fx = q.tiles_x - (has_c ? 1 : 0);
+            q.fy = q.tiles_y - (has_r ? 1 : 0);
+            q.nF = N * q.fx * q.fy;
+            q.nC = has_c ? N * q.fy : 0;
+            q.nR = has_r ? N * q.tiles_x : 0;
+            q.startC = (q.nF + 1) / 2 * 2;
+            q.startR = q.startC + (q.nC + 1) / 2 * 2;
+            q.m_tiles = q.startR + q.nR;                       // class padding included
+            q.m_pairs = (q.m_tiles + 1) / 2;
         }
-        // pairs whose first tile is a full one cost two halves, the rest one
-        q.n_full_pairs = std::min(q.m_pairs, (q.N * q.n_full_img + 1) / 2);
+        // pairs of class F cost two halves, the rest one
+        q.n_full_pairs = small ? q.m_pairs : q.startC / 2;
         pairs += q.m_pairs * q.n_tiles_n;
 
         cuuint64_t adims[4] = {(cuuint64_t)op.in.c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};

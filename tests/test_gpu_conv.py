@@ -38,6 +38,11 @@ CASES = [
     (1, 92, 164, 128, 128, 7, True, False, False),   # s=2.0 stage layer: 3 waves of tiles
     (2, 50, 70, 64, 64, 3, True, False, False),      # conv1_2 shape class (see test_conv_pair_resident_variant)
     (1, 184, 328, 64, 64, 3, True, True, False),     # conv1_2 at scale 0.5 with its fused pool
+    (2, 23, 23, 128, 128, 3, True, False, False),    # hand map: last tile column AND last tile row are half tiles (mixed orientations)
+    (1, 69, 69, 192, 128, 7, True, False, False),    # the same at 7x7
+    (2, 72, 40, 128, 128, 3, True, True, False),     # 8 rows left in the last tile row, with the fused pool
+    (3, 8, 8, 128, 128, 3, True, False, True),       # a single half tile per image (odd tile count: padding tile in the pair)
+    (1, 40, 72, 128, 256, 3, True, False, False),    # 8 columns left in the last tile column, two N tiles
 ]
 
 
