@@ -208,10 +208,17 @@ int opb_smooth_debug(opb_context* ctx, const float* dev_heat, int parts, int hei
 
 /* Debug/cross-check: generic convolution on NHWC bf16 device tensors through either the tcgen05
  * implicit-GEMM path the networks use (impl = 0), the scalar reference kernel (impl = 1), or a specific
- * tensor-core variant (2 = per-tap tiles, 3 / 4 = patch-resident MODE 0 / 1, 5 = CTA pair).  weight is host OIHW fp32.
+ * tensor-core variant (2 = per-tap tiles, 3 / 4 = patch-resident MODE 0 / 1, 5 = CTA pair, 6 = CTA pair in the
+ * wide-pixel pooled form the networks use for conv1_2: cin = cout = 64, k = 3, pool != 0).  weight is host OIHW fp32.
  * out_fp32 != 0 writes fp32.  pool != 0 fuses a 2x2/2 max-pool (impl 0 only).                         */
 int opb_conv2d(opb_context* ctx, const void* dev_in_bf16, int n, int h, int w, int cin, const float* weight,
                const float* bias, int cout, int k, int relu, int pool, int out_fp32, void* dev_out, int impl);
+
+/* Host only (no device call): the wide-pixel weights of a 64 -> 64 channel 3x3 layer (src/model.py:36 conv1_2) as the
+ * library packs them at opb_net_finalize.  weight: [64][64][3][3] fp32, bias [64]  ->  w_wide [128][9][128] bf16 bit
+ * patterns (output column = parity_out * 64 + cout; K index = (dy * 3 + di) * 128 + parity_in * 64 + cin, di the tap in
+ * units of column PAIRS), b_wide [128].  Lets a CPU test prove the re-described layer equals the original one.        */
+int opb_wide_pool_weights(const float* weight, const float* bias, unsigned short* w_wide, float* b_wide);
 
 #ifdef __cplusplus
 }

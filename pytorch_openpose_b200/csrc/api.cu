@@ -1693,6 +1693,17 @@ int opb_hand_peaks(opb_context* ctx, const float* dev_heat, int H, int W, double
     });
 }
 
+int opb_wide_pool_weights(const float* weight, const float* bias, unsigned short* w_wide, float* b_wide) {
+    return guarded([&] {
+        OPB_REQUIRE(weight && bias && w_wide && b_wide, "opb_wide_pool_weights: null argument");
+        std::vector<__nv_bfloat16> ww;
+        std::vector<float> bw;
+        wide_pool_weights(weight, bias, ww, bw);
+        memcpy(w_wide, ww.data(), ww.size() * sizeof(__nv_bfloat16));
+        memcpy(b_wide, bw.data(), bw.size() * sizeof(float));
+    });
+}
+
 int opb_conv2d(opb_context* ctx, const void* dev_in, int n, int h, int w, int cin, const float* weight, const float* bias,
                int cout, int k, int relu, int pool, int out_fp32, void* dev_out, int impl) {
     return guarded([&] {
