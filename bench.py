@@ -383,7 +383,7 @@ def run_ours(args):
         except Exception:
             pass
         roof = {"bound": "tensor",
-                "kernel": "tcgen05 implicit-GEMM conv, N=128 variants (conv_pair_kernel<128> cta_group::2 for 3x3/7x7, conv_tc_kernel<128> for 1x1): "
+                "kernel": "tcgen05 implicit-GEMM conv, N=128 variants (conv_pair_kernel<128> cta_group::2 for 3x3/7x7 incl. conv1_2 in its wide-pixel form, conv_tc_kernel<128> for 1x1): "
                           "mean over its %d launches per batch of %d frames" % (tc_n // n_prof, B),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": how,
                 "traffic": traffic, "traffic_note": "DRAM bytes of the ncu-captured 7x7 stage launch (profiles/roofline_traffic.json)",

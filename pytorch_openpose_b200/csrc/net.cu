@@ -344,7 +344,7 @@ struct Builder {
                                                                 : conv_tc_plan(ops, bn, net->ctx->num_sms);
             plan->launches.push_back(L);
             plan->steps.push_back([L](cudaStream_t s) { conv_tc_plan_run(L, s); });
-            plan->step_names.push_back(std::string(bn == 128 ? "conv_tc128:" : "conv_tc64:") + names[first]);
+            plan->step_names.push_back(std::string(bn_run == 128 ? "conv_tc128:" : "conv_tc64:") + names[first]);   // the N tile that runs
             plan->step_gflop.push_back(gf);
             plan->kernel_launches += 1;
         }
