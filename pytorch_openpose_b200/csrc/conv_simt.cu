@@ -99,6 +99,12 @@ __device__ __forceinline__ uint32_t pack_norm(uint8_t lo, uint8_t hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn((float)lo * (1.0f / 256.0f) - 0.5f, (float)hi * (1.0f / 256.0f) - 0.5f);
     return *(const uint32_t*)&h;
 }
+// max(x, 0) rounded to bf16, two at a time (one F2FP.RELU instead of two FMNMX + F2FP); lo -> low half
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
     asm volatile(
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -181,10 +187,19 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
     // completely inside the image row or completely outside (then it stages zeros: the padding).
     uint32_t pre[3][kLoadsPerRow];
     unsigned pre_valid = 0;
-    auto fetch = [&](int seg) {
-        const int sx = seg % segs_per_row;
-        const int y = (seg / segs_per_row) % H;
-        const size_t img = seg / (segs_per_row * H);
+    // (segment in row, row, image) of a segment index without divisions in the loop: the grid stride is a fixed number
+    // of rows plus a fixed number of segments
+    struct Pos { int sx, y, img; };
+    const int step_rows = (int)gridDim.x / segs_per_row, step_sx = (int)gridDim.x - step_rows * segs_per_row;
+    auto advance = [&](Pos& q) {
+        q.sx += step_sx;
+        q.y += step_rows;
+        if (q.sx >= segs_per_row) { q.sx -= segs_per_row; ++q.y; }
+        while (q.y >= H) { q.y -= H; ++q.img; }
+    };
+    auto fetch = [&](const Pos& q) {
+        const int sx = q.sx, y = q.y;
+        const size_t img = (size_t)q.img;
         const int first = (sx * kSegPx - 1) * 3 - 1;                 // flat element index of staged element 0
         pre_valid = 0;
 #pragma unroll
@@ -201,12 +216,19 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
             }
         }
     };
-    if ((int)blockIdx.x < total_segs) fetch(blockIdx.x);
+    Pos nxt;
+    nxt.sx = (int)blockIdx.x % segs_per_row;
+    nxt.y = ((int)blockIdx.x / segs_per_row) % H;
+    nxt.img = (int)blockIdx.x / (segs_per_row * H);
+    if ((int)blockIdx.x < total_segs) fetch(nxt);
+    // swizzled read position of this thread in the staged output tile (the same for all 8 store passes)
+    const int st_rd = ((int)threadIdx.x & ~7) + (((int)threadIdx.x & 7) ^ (((int)threadIdx.x >> 3) & 7));
 
     for (int seg = blockIdx.x; seg < total_segs; seg += gridDim.x) {
-        const int sx = seg % segs_per_row;
-        const int y = (seg / segs_per_row) % H;
-        const size_t img = seg / (segs_per_row * H);
+        const Pos cur = nxt;
+        advance(nxt);
+        const int sx = cur.sx, y = cur.y;
+        const size_t img = (size_t)cur.img;
         const int x0 = sx * kSegPx;
         const int npx = min(kSegPx, W - x0);
         __syncthreads();                                   // previous iteration finished with srow / stile
@@ -219,7 +241,7 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
                     stage_word(&srow[r][wi * kPer], pre[r][q], (pre_valid >> (r * kLoadsPerRow + q)) & 1u, T());
             }
         __syncthreads();
-        if (seg + (int)gridDim.x < total_segs) fetch(seg + gridDim.x);
+        if (seg + (int)gridDim.x < total_segs) fetch(nxt);
         // A fragments of both 16-pixel tiles and both k steps (16 registers), then two passes over the 64 output
         // channels (32 accumulators live at a time keeps the kernel at 4 CTAs per SM)
         uint32_t afrag[2][2][4];
@@ -265,8 +287,7 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
 #pragma unroll
                     for (int jj = 0; jj < 4; ++jj) {
                         const int j = jh * 4 + jj;
-                        const __nv_bfloat162 h2 = __floats2bfloat162_rn(fmaxf(acc[mt][jj][hr * 2], 0.f), fmaxf(acc[mt][jj][hr * 2 + 1], 0.f));
-                        st32[(p * 8 + (j ^ (p & 7))) * 4 + t] = *(const uint32_t*)&h2;
+                        st32[(p * 8 + (j ^ (p & 7))) * 4 + t] = pack_relu_bf16x2(acc[mt][jj][hr * 2], acc[mt][jj][hr * 2 + 1]);
                     }
                 }
         }
@@ -277,7 +298,7 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int q = i * 128 + threadIdx.x;               // pixel = q / 8, chunk = q % 8
-                if ((q >> 3) < npx) o[q] = stile[(q & ~7) + ((q & 7) ^ ((q >> 3) & 7))];
+                if ((q >> 3) < npx) o[q] = stile[i * 128 + st_rd]; // (q & ~7) + ((q & 7) ^ ((q >> 3) & 7)), i * 16 = 0 mod 8
             }
         } else if ((int)threadIdx.x < npx) {
             uint4* o = (uint4*)(out + (pix0 + threadIdx.x) * out_cstride);
