@@ -231,7 +231,8 @@ __global__ void __launch_bounds__(128, 4) conv_first_mma_kernel(const T* __restr
         const size_t img = (size_t)cur.img;
         const int x0 = sx * kSegPx;
         const int npx = min(kSegPx, W - x0);
-        __syncthreads();                                   // previous iteration finished with srow / stile
+        // no barrier here: srow was last read before the barrier that precedes the previous store pass, and stile is
+        // written only after the next barrier, which every thread reaches after its store pass
 #pragma unroll
         for (int r = 0; r < 3; ++r)
 #pragma unroll
