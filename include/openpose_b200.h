@@ -220,6 +220,13 @@ int opb_conv2d(opb_context* ctx, const void* dev_in_bf16, int n, int h, int w, i
  * units of column PAIRS), b_wide [128].  Lets a CPU test prove the re-described layer equals the original one.        */
 int opb_wide_pool_weights(const float* weight, const float* bias, unsigned short* w_wide, float* b_wide);
 
+/* Host only (no device call): the tile list of the CTA-pair convolution kernel for one problem of n images of h x w
+ * pixels, exactly as the kernel decodes it -- 8 ints per (pair, cluster rank): image, x0, y0, n0, real (0 = padding tile,
+ * computed but never stored), halves (bit h: 128-pixel half h holds pixels), vsplit (0 = halves side by side 8 x 16,
+ * 1 = stacked 16 x 8), full_cost.  small != 0: the 16 x 8 tiles of launches that fill few SMs.  For the CPU test of
+ * the tiling (every pixel stored exactly once, both tiles of a pair share one orientation).  *written = entries.     */
+int opb_debug_pair_tiles(int n, int h, int w, int n_tiles_n, int small, int* out, int cap, int* written);
+
 #ifdef __cplusplus
 }
 #endif

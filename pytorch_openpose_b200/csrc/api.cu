@@ -1693,6 +1693,15 @@ int opb_hand_peaks(opb_context* ctx, const float* dev_heat, int H, int W, double
     });
 }
 
+int opb_debug_pair_tiles(int n, int h, int w, int n_tiles_n, int small, int* out, int cap, int* written) {
+    return guarded([&] {
+        OPB_REQUIRE(out && written && n >= 1 && h >= 1 && w >= 1 && n_tiles_n >= 1, "opb_debug_pair_tiles: bad argument");
+        const int r = conv_pair_debug_tiles(n, h, w, n_tiles_n, small, out, cap);
+        if (r < 0) throw Error(OPB_ERR_CAPACITY, "opb_debug_pair_tiles: output too small");
+        *written = r;
+    });
+}
+
 int opb_wide_pool_weights(const float* weight, const float* bias, unsigned short* w_wide, float* b_wide) {
     return guarded([&] {
         OPB_REQUIRE(weight && bias && w_wide && b_wide, "opb_wide_pool_weights: null argument");

@@ -110,7 +110,7 @@ struct TileCoord {
     int halves;                  // bit h: half h of the super-tile holds at least one pixel of the image
     int vsplit;                  // orientation of this tile (QProb::vsplit for class F, 0 for C, 1 for R)
 };
-__device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, int rank, int block_n) {
+__host__ __device__ __forceinline__ TileCoord decode_pair(const PairParams& p, int pr, int rank, int block_n) {
     int pi = 0, local;
     if (pr < p.total_full) {
         while (pi + 1 < p.nprob && pr >= p.prob[pi + 1].pair_begin) ++pi;
@@ -539,6 +539,56 @@ conv_pair_kernel(const __grid_constant__ PairParams p) {
     cluster_sync_all();
 }
 
+// Tile classes and pair counts of one problem (q.H, q.W, q.N set).
+void fill_tiling(QProb& q, bool small, bool resident) {
+    const int H = q.H, W = q.W, N = q.N;
+    q.tile_h = small ? 8 : kTile;
+    q.tiles_x = cdiv(W, kTile);
+    q.tiles_y = cdiv(H, q.tile_h);
+    {
+        // 128-pixel halves actually multiplied.  A tile with pixels in both halves costs 256 rows whatever its
+        // orientation; the last tile column is split side by side when at most 8 columns remain there, the last tile
+        // row stacked when at most 8 rows remain, and their empty half is skipped: columns and rows both round up to 8
+        // (41x23: 48x24, 82x46: 88x48, 69x69: 72x72, 23x23: 24x24).  OPB_PAIR_NO_MIXED=1: one orientation per problem
+        // (the one with the least padding), i.e. only one of the two edges profits.
+        static const char* force = getenv("OPB_PAIR_SPLIT");
+        static const char* noskip = getenv("OPB_PAIR_NOSKIP");
+        static const bool mixed = getenv("OPB_PAIR_NO_MIXED") == nullptr;
+        const long side = (long)cdiv(W, 8) * 8 * cdiv(H, 16) * 16, stacked = (long)cdiv(W, 16) * 16 * cdiv(H, 8) * 8;
+        q.vsplit = small ? 1 : (resident ? 0 : (force ? atoi(force) : (stacked < side ? 1 : 0)));   // 24-column patches: side by side only
+        q.noskip = noskip ? 1 : 0;
+        const bool skip = !small && !q.noskip;
+        const bool has_c = skip && (q.tiles_x - 1) * kTile + 8 >= W && (mixed || q.vsplit == 0);
+        const bool has_r = skip && (q.tiles_y - 1) * kTile + 8 >= H && !resident && (mixed || q.vsplit == 1);
+        q.fx = q.tiles_x - (has_c ? 1 : 0);
+        q.fy = q.tiles_y - (has_r ? 1 : 0);
+        q.nF = N * q.fx * q.fy;
+        q.nC = has_c ? N * q.fy : 0;
+        q.nR = has_r ? N * q.tiles_x : 0;
+        q.startC = (q.nF + 1) / 2 * 2;
+        q.startR = q.startC + (q.nC + 1) / 2 * 2;
+        q.m_tiles = q.startR + q.nR;                       // class padding included
+        q.m_pairs = (q.m_tiles + 1) / 2;
+    }
+    // pairs of class F cost two halves, the rest one
+    q.n_full_pairs = small ? q.m_pairs : q.startC / 2;
+}
+
+// launch order: the full-cost pairs of every problem, then the half-cost pairs of every problem
+int order_pairs(PairParams& P) {
+    int at = 0;
+    for (int i = 0; i < P.nprob; ++i) {
+        P.prob[i].pair_begin = at;
+        at += P.prob[i].n_full_pairs * P.prob[i].n_tiles_n;
+    }
+    P.total_full = at;
+    for (int i = 0; i < P.nprob; ++i) {
+        P.prob[i].edge_begin = at;
+        at += (P.prob[i].m_pairs - P.prob[i].n_full_pairs) * P.prob[i].n_tiles_n;
+    }
+    return at;
+}
+
 struct PairLaunch : ConvLaunch {
     PairParams params;
     int grid = 0, block_n = 128;
@@ -644,42 +694,13 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
         q.out = op.out.ptr();
         q.bias = op.bias;
         q.H = H; q.W = W; q.N = N;
-        q.tile_h = small ? 8 : kTile;
-        q.tiles_x = cdiv(W, kTile);
-        q.tiles_y = cdiv(H, q.tile_h);
         q.out_cstride = op.out.cstride;
         q.cout_store = op.cout_store;
         q.n_tiles_n = op.cout_pad / block_n;
         q.cin_chunks = op.in.c / 64;
         q.flags = (op.relu ? FLAG_RELU : 0) | (op.out.elem == 4 ? FLAG_F32 : 0) | (op.pool ? FLAG_POOL : 0) |
                   (op.pool_wide ? FLAG_POOLW : 0);
-        {
-            // 128-pixel halves actually multiplied.  A tile with pixels in both halves costs 256 rows whatever its
-            // orientation; the last tile column is split side by side when at most 8 columns remain there, the last tile
-            // row stacked when at most 8 rows remain, and their empty half is skipped: columns and rows both round up to 8
-            // (41x23: 48x24, 82x46: 88x48, 69x69: 72x72, 23x23: 24x24).  OPB_PAIR_NO_MIXED=1: one orientation per problem
-            // (the one with the least padding), i.e. only one of the two edges profits.
-            static const char* force = getenv("OPB_PAIR_SPLIT");
-            static const char* noskip = getenv("OPB_PAIR_NOSKIP");
-            static const bool mixed = getenv("OPB_PAIR_NO_MIXED") == nullptr;
-            const long side = (long)cdiv(W, 8) * 8 * cdiv(H, 16) * 16, stacked = (long)cdiv(W, 16) * 16 * cdiv(H, 8) * 8;
-            q.vsplit = small ? 1 : (resident ? 0 : (force ? atoi(force) : (stacked < side ? 1 : 0)));   // 24-column patches: side by side only
-            q.noskip = noskip ? 1 : 0;
-            const bool skip = !small && !q.noskip;
-            const bool has_c = skip && (q.tiles_x - 1) * kTile + 8 >= W && (mixed || q.vsplit == 0);
-            const bool has_r = skip && (q.tiles_y - 1) * kTile + 8 >= H && !resident && (mixed || q.vsplit == 1);
-            q.fx = q.tiles_x - (has_c ? 1 : 0);
-            q.fy = q.tiles_y - (has_r ? 1 : 0);
-            q.nF = N * q.fx * q.fy;
-            q.nC = has_c ? N * q.fy : 0;
-            q.nR = has_r ? N * q.tiles_x : 0;
-            q.startC = (q.nF + 1) / 2 * 2;
-            q.startR = q.startC + (q.nC + 1) / 2 * 2;
-            q.m_tiles = q.startR + q.nR;                       // class padding included
-            q.m_pairs = (q.m_tiles + 1) / 2;
-        }
-        // pairs of class F cost two halves, the rest one
-        q.n_full_pairs = small ? q.m_pairs : q.startC / 2;
+        fill_tiling(q, small, resident);
         pairs += q.m_pairs * q.n_tiles_n;
 
         cuuint64_t adims[4] = {(cuuint64_t)op.in.c, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
@@ -706,26 +727,38 @@ ConvLaunch* conv_pair_plan(const std::vector<ConvOp>& ops, int block_n, int num_
             }
         if (same && bytes <= (long)9 * (block_n / 2) * 128) P.bres = (int)bytes;
     }
-    // launch order: the full-cost pairs of every problem, then the half-cost pairs of every problem
-    {
-        int at = 0;
-        for (int i = 0; i < P.nprob; ++i) {
-            P.prob[i].pair_begin = at;
-            at += P.prob[i].n_full_pairs * P.prob[i].n_tiles_n;
-        }
-        P.total_full = at;
-        for (int i = 0; i < P.nprob; ++i) {
-            P.prob[i].edge_begin = at;
-            at += (P.prob[i].m_pairs - P.prob[i].n_full_pairs) * P.prob[i].n_tiles_n;
-        }
-        OPB_REQUIRE(at == pairs, "conv_pair: pair order");
-    }
+    OPB_REQUIRE(order_pairs(P) == pairs, "conv_pair: pair order");
     P.total_pairs = pairs;
     L->tiles = pairs * 2;
     L->block_n = block_n;
     const int clusters = pairs < num_sms / 2 ? pairs : num_sms / 2;
     L->grid = clusters * 2;
     return L.release();
+}
+
+// Host only: the tile list of one problem as the kernel decodes it -- 8 ints per (pair, rank): image, x0, y0, n0, real,
+// halves, vsplit, full-cost flag.  For the CPU test of the tiling (exact cover, pairs share an orientation).
+int conv_pair_debug_tiles(int n, int h, int w, int n_tiles_n, int small, int* out, int cap) {
+    PairParams P;
+    memset(&P, 0, sizeof(P));
+    P.nprob = 1;
+    P.ks = 3;
+    QProb& q = P.prob[0];
+    q.H = h; q.W = w; q.N = n;
+    q.n_tiles_n = n_tiles_n;
+    fill_tiling(q, small != 0, false);
+    P.total_pairs = order_pairs(P);
+    int written = 0;
+    for (int pr = 0; pr < P.total_pairs; ++pr)
+        for (int rank = 0; rank < 2; ++rank) {
+            const TileCoord c = decode_pair(P, pr, rank, 128);
+            if ((written + 1) * 8 > cap) return -1;
+            int* o = out + written * 8;
+            o[0] = c.img; o[1] = c.x0; o[2] = c.y0; o[3] = c.n0; o[4] = c.real ? 1 : 0; o[5] = c.halves; o[6] = c.vsplit;
+            o[7] = pr < P.total_full ? 1 : 0;
+            ++written;
+        }
+    return written;
 }
 
 }  // namespace opb

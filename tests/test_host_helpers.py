@@ -1,5 +1,6 @@
 """Host-side helpers that need no GPU."""
 import numpy as np
+from hypothesis import given, settings, strategies as st
 
 from oracle import openpose_oracle as O
 
@@ -69,3 +70,74 @@ def test_wide_pixel_weights_describe_the_same_layer():
             out += a @ wwf[:, dy, di].reshape(128, 128).astype(np.float64).T
     out += bw
     assert np.allclose(out.reshape(H, W // 2, 2, 64).reshape(H, W, 64), ref, rtol=0, atol=1e-9)
+
+
+def _pair_tiles(n, h, w, n_tiles_n=1, small=0):
+    import ctypes
+    from pytorch_openpose_b200 import _lib
+    cap = 8 * 4 * (n * ((h + 7) // 8) * ((w + 15) // 16) + 8) * n_tiles_n
+    out = np.zeros(cap, dtype=np.int32)
+    written = ctypes.c_int(0)
+    _lib.check(_lib.lib().opb_debug_pair_tiles(n, h, w, n_tiles_n, small, out.ctypes.data, cap, ctypes.byref(written)))
+    return out[:written.value * 8].reshape(-1, 2, 8)           # (pair, rank, fields)
+
+
+def _check_tiling(n, h, w, n_tiles_n=1, small=0):
+    """Every pixel of every image is stored by exactly one (tile, half) per N tile; the two tiles of a pair share N tile and
+    orientation (the pair's single A descriptor); the halves the pair multiplies are a superset of what each tile stores."""
+    t = _pair_tiles(n, h, w, n_tiles_n, small)
+    cover = np.zeros((n_tiles_n, n, h, w), dtype=np.int32)
+    multiplied = own = 0
+    for pair in t:
+        live = [r for r in pair if r[4]]
+        assert live, "a pair of two padding tiles"
+        assert len({(r[3], r[6]) for r in pair}) == 1, "tiles of a pair differ in N tile or orientation"
+        halves = pair[0][5] | pair[1][5]
+        multiplied += 2 * bin(halves).count("1") * 128
+        for img, x0, y0, n0, real, hv, vs, full in pair:
+            if not real:
+                assert hv == 0
+                continue
+            own += bin(hv).count("1") * 128
+            th = 8 if small else 16
+            for hh in range(2):
+                if not (hv >> hh) & 1:
+                    continue
+                if small:
+                    xs, ys, ww, hhh = x0, y0, 16, 8
+                elif vs:
+                    xs, ys, ww, hhh = x0, y0 + 8 * hh, 16, 8
+                else:
+                    xs, ys, ww, hhh = x0 + 8 * hh, y0, 8, 16
+                cover[n0 // 128, img, ys:min(ys + hhh, h), xs:min(xs + ww, w)] += 1
+            assert y0 % th == 0 and x0 % 16 == 0
+    assert (cover == 1).all(), "pixels stored %d..%d times" % (cover.min(), cover.max())
+    total = float(n_tiles_n * n * h * w)
+    return own / total, multiplied / total       # rows of the halves that hold pixels / rows the pairs actually multiply
+
+
+def test_conv_pair_tiling_covers_every_pixel_once():
+    """The tile decode of the CTA-pair kernel (host copy of the device function), over the shapes the networks produce and
+    a sweep of small ones: exact cover, consistent pairs, and the padding the design document quotes."""
+    body = [(23, 41), (46, 82), (69, 123), (92, 164)]
+    hand = [(23, 23), (46, 46), (69, 69), (92, 92)]
+    for n in (1, 3, 8):
+        for h, w in body + hand:
+            _check_tiling(n, h, w)
+    pix = lambda shapes: float(sum(h * w for h, w in shapes))
+    ratio = lambda shapes, n, k: sum(_check_tiling(n, h, w)[k] * h * w for h, w in shapes) / pix(shapes)
+    assert abs(ratio(body, 1, 0) - 1.086) < 2e-3 and abs(ratio(hand, 1, 0) - 1.097) < 2e-3      # DESIGN.md 4b
+    # what pairing adds on top (a half one tile of a pair needs is multiplied for both; class padding tiles)
+    assert ratio(body, 8, 1) < 1.10 and ratio(hand, 16, 1) < 1.10
+    for h in range(1, 41):
+        for w in range(1, 41):
+            _check_tiling(2, h, w)
+    for h, w in [(8, 8), (9, 17), (16, 16), (24, 24), (33, 8), (8, 33)]:
+        _check_tiling(3, h, w, n_tiles_n=2)
+        _check_tiling(1, h, w, small=1)
+
+
+@settings(max_examples=60, deadline=None)
+@given(st.integers(1, 9), st.integers(1, 200), st.integers(1, 200), st.integers(1, 4), st.booleans())
+def test_conv_pair_tiling_property(n, h, w, n_tiles_n, small):
+    _check_tiling(n, h, w, n_tiles_n, int(small))
