@@ -243,12 +243,15 @@ def extra_e2e_decode(local, rank, barrier, max_over_ranks, world, n_frames=256):
     quiet = lambda m: None
     extract.extract_motion_from_video(path, os.path.join(d, "w.pkl"), None, body, mode="body", batch=8, sessions=3,
                                       log=quiet, decode_workers=workers)                  # plans + pinned rings
-    barrier()
-    t0 = time.perf_counter()
-    mat = extract.extract_motion_from_video(path, os.path.join(d, "o.pkl"), None, body, mode="body", batch=8, sessions=3,
-                                            log=quiet, decode_workers=workers)
-    torch.cuda.synchronize()
-    dt = max_over_ranks(time.perf_counter() - t0)
+    passes = []
+    for rep in range(3):                # 256 frames take ~0.8 s of wall clock: one hiccup of the host is 20 % -> median of 3 passes
+        barrier()
+        t0 = time.perf_counter()
+        mat = extract.extract_motion_from_video(path, os.path.join(d, "o%d.pkl" % rep), None, body, mode="body", batch=8,
+                                                sessions=3, log=quiet, decode_workers=workers)
+        torch.cuda.synchronize()
+        passes.append(max_over_ranks(time.perf_counter() - t0))
+    dt = sorted(passes)[1]
     # decode alone, same threads, all ranks at once
     barrier()
     t0 = time.perf_counter()
@@ -258,7 +261,9 @@ def extra_e2e_decode(local, rank, barrier, max_over_ranks, world, n_frames=256):
     shutil.rmtree(d, ignore_errors=True)
     return {"value": round(len(mat) * world / dt, 1), "unit": "frames/s", "decode_only_frames_per_s": round(n * world / ddt, 1),
             "decoder_threads_per_rank": workers, "host_cores": os.cpu_count(), "frames_per_rank": int(len(mat)),
-            "workload": "720p MJPG file per rank -> decode threads -> pinned ring -> Body 4-scale -> pose track file; wall clock"}
+            "passes_frames_per_s": [round(len(mat) * world / t, 1) for t in passes],
+            "workload": "720p MJPG file per rank -> decode threads -> pinned ring -> Body 4-scale -> pose track file; "
+                        "wall clock, median of 3 passes"}
 
 
 def run_ours(args):
