@@ -203,10 +203,10 @@ def test_multiscale_average_in_float32_is_a_tolerance_level_deviation():
 
 
 def test_fuzz_random_sizes_and_scales():
-    """tools/fuzz_body.py (random frame sizes 12..520, scale lists, single frames and batches, structured and flat
+    """tests/tools/fuzz_body.py (random frame sizes 12..520, scale lists, single frames and batches, structured and flat
     weights): discrete results equal the oracle's post-processing of the device maps in every case."""
     import subprocess
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, "tools", "fuzz_body.py"), "10", "5"], cwd=root,
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "fuzz_body.py"), "10", "5"], cwd=root,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "10 cases, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -11,7 +11,7 @@ import time
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle import openpose_oracle as O                        # noqa: E402
 from pytorch_openpose_b200 import Batch_body, Batch_hand       # noqa: E402
 

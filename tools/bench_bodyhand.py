@@ -13,7 +13,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import openpose_oracle as O            # noqa: E402  (random-init weights)
+from pytorch_openpose_b200.model import random_checkpoint      # noqa: E402  (random-init weights; no checkpoints offline)
 from pytorch_openpose_b200 import Body, Hand       # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -29,8 +29,8 @@ if world > 1:
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 H, W, B, F = 720, 1280, args.batch, args.frames_per_step
-body = Body(O.make_weights("body", 0), scale_search=[0.5, 1.0, 1.5, 2.0], device=local)
-hand = Hand(O.make_weights("hand", 0), device=local)
+body = Body(random_checkpoint("body", 0), scale_search=[0.5, 1.0, 1.5, 2.0], device=local)
+hand = Hand(random_checkpoint("hand", 0), device=local)
 bs = [body.net.session() for _ in range(args.streams)]
 hs = [hand.net.session() for _ in range(args.streams)]
 rng = np.random.default_rng(rank)

@@ -11,7 +11,7 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import cv2                                              # noqa: E402
-from oracle import openpose_oracle as O                # noqa: E402
+from pytorch_openpose_b200.model import random_checkpoint      # noqa: E402  (random-init weights; no checkpoints offline)
 from pytorch_openpose_b200 import Body, Batch_body, extract   # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 384
@@ -32,7 +32,7 @@ for k in (1, W):
     n = sum(len(f) for f, _ in extract.FrameBatches(path, None, batch=8, depth=5, pinned=True, workers=k))
     dec[k] = n / (time.perf_counter() - t0)
 
-body = Body(O.make_weights("body", 0), scale_search=[0.5, 1.0, 1.5, 2.0])
+body = Body(random_checkpoint("body", 0), scale_search=[0.5, 1.0, 1.5, 2.0])
 extract.extract_motion_from_video(path, os.path.join(d, "w.pkl"), None, body, mode="body", batch=8, sessions=3,
                                   log=lambda m: None)                      # warm-up: plans
 job = {}
@@ -72,8 +72,8 @@ class BodyP(Body):
         return [self._person() for _ in Body.collect_batch(self, session)]
 
 
-bodyp = BodyP(body.net_weights if hasattr(body, "net_weights") else O.make_weights("body", 0), scale_search=[0.5, 1.0, 1.5, 2.0])
-hand = Hand(O.make_weights("hand", 0))
+bodyp = BodyP(body.net_weights if hasattr(body, "net_weights") else random_checkpoint("body", 0), scale_search=[0.5, 1.0, 1.5, 2.0])
+hand = Hand(random_checkpoint("hand", 0))
 bh = {}
 for k in (W,):
     extract.extract_motion_from_video(path, os.path.join(d, "wh.pkl"), None, bodyp, hand, mode="bodyhand", batch=8,
@@ -85,7 +85,7 @@ for k in (W,):
     bh["frames_with_both_hands"] = int(((mat[:, 18:39, 2] > 0).any(1) & (mat[:, 39:, 2] > 0).any(1)).sum())
 del bodyp, hand
 del body
-bb = Batch_body(O.make_weights("body", 0))
+bb = Batch_body(random_checkpoint("body", 0))
 extract.batch_body_extraction(path, os.path.join(d, "wb.pkl"), 16, None, bb, log=lambda m: None)
 bjob = {}
 for k in (1, W):

@@ -6,12 +6,12 @@ import time
 import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import openpose_oracle as O            # noqa: E402
+from pytorch_openpose_b200.model import random_checkpoint      # noqa: E402  (random-init weights; no checkpoints offline)
 from pytorch_openpose_b200 import Hand             # noqa: E402
 
 batch = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 scales = [0.5, 1.0, 1.5, 2.0] if len(sys.argv) < 3 else [float(s) for s in sys.argv[2].split(",")]
-hand = Hand(O.make_weights("hand", 0), scale_search=scales)
+hand = Hand(random_checkpoint("hand", 0), scale_search=scales)
 crops = np.random.default_rng(0).integers(0, 256, (batch, 368, 368, 3), dtype=np.uint8)
 s = hand._session
 for _ in range(2):

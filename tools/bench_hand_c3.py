@@ -10,13 +10,13 @@ import faulthandler
 faulthandler.dump_traceback_later(int(os.environ.get("OPB_DBG_TIMEOUT", "50")), exit=True)
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import openpose_oracle as O            # noqa: E402
+from pytorch_openpose_b200.model import random_checkpoint      # noqa: E402  (random-init weights; no checkpoints offline)
 from pytorch_openpose_b200 import Hand             # noqa: E402
 
 crops = np.random.default_rng(0).integers(0, 256, (256, 368, 368, 3), dtype=np.uint8)
 res = {}
 for tag, scales, gflop in (("4scale", [0.5, 1.0, 1.5, 2.0], 1547.82), ("1scale", [1.0], 206.38)):
-    hand = Hand(O.make_weights("hand", 0), scale_search=scales)
+    hand = Hand(random_checkpoint("hand", 0), scale_search=scales)
     hand(crops)                                     # warm-up: builds the plans
     torch.cuda.synchronize()
     t0 = time.perf_counter()

@@ -9,13 +9,13 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import openpose_oracle as O            # noqa: E402
+from pytorch_openpose_b200.model import random_checkpoint      # noqa: E402  (random-init weights; no checkpoints offline)
 from pytorch_openpose_b200 import Hand             # noqa: E402
 
 rng = np.random.default_rng(0)
 sizes = list(range(150, 270, 2))
 crops = [rng.integers(0, 256, (w, w, 3), dtype=np.uint8) for w in sizes]
-hand = Hand(O.make_weights("hand", 0))
+hand = Hand(random_checkpoint("hand", 0))
 hand(crops[0])
 torch.cuda.synchronize()
 free0 = torch.cuda.mem_get_info()[0]

@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from oracle import openpose_oracle as O            # noqa: E402
+from pytorch_openpose_b200.model import random_checkpoint      # noqa: E402  (random-init weights; no checkpoints offline)
 from pytorch_openpose_b200 import Body, Hand       # noqa: E402
 
 rng = np.random.default_rng(0)
@@ -29,11 +29,11 @@ def lat(fn, inputs, reps=60):
     return {"ms_median": float(np.median(t)), "ms_p90": float(np.percentile(t, 90)), "calls_per_s": 1e3 / float(np.median(t))}
 
 
-sd = O.make_weights("body", 0)
+sd = random_checkpoint("body", 0)
 res["body_c1_640x480_scale0.5"] = lat(Body(sd), [rng.integers(0, 256, (480, 640, 3), dtype=np.uint8) for _ in range(8)])
 res["body_c2_720p_4scale"] = lat(Body(sd, scale_search=[0.5, 1.0, 1.5, 2.0]),
                                  [rng.integers(0, 256, (720, 1280, 3), dtype=np.uint8) for _ in range(8)])
-hand = Hand(O.make_weights("hand", 0))
+hand = Hand(random_checkpoint("hand", 0))
 res["hand_184_4scale"] = lat(hand, [rng.integers(0, 256, (184, 184, 3), dtype=np.uint8) for _ in range(8)])
 res["hand_changing_size_4scale"] = lat(hand, [rng.integers(0, 256, (w, w, 3), dtype=np.uint8) for w in range(150, 214, 8)])
 print(json.dumps({"metric": "synchronous_call_latency", "results": res}))
