@@ -6,11 +6,17 @@
 // TMEM accumulator) and only HALF of the weight tile (N/2 rows), so per SM the operand reads drop to 6 KB per 64
 // cycles and the weight traffic L2->SM halves.
 //
-//   cluster (2,1,1): CTA rank r owns super-tile 2*pair + r of a problem (same weights, same n tile).
-//   leader (rank 0) : arms the full barriers for the bytes of BOTH CTAs, issues every tcgen05.mma.cta_group::2 and
-//                     commits with .multicast::cluster so the empty / accumulator-full barriers of both CTAs fire.
+//   cluster (2,1,1): CTA rank r owns super-tile 2*pair + r of a problem (same weights, same n tile, same orientation).
+//   leader (rank 0) : arms the full barriers for the bytes of BOTH CTAs, issues every tcgen05.mma.cta_group::2 -- two
+//                     issuer warps, one per 128-pixel half of the super-tiles -- and commits with .multicast::cluster so
+//                     the empty / accumulator-full barriers of both CTAs fire (two arrivals each, one per issuer).
 //   both CTAs       : TMA producers (patches + their half of the weights; complete_tx goes to the leader's barrier),
 //                     epilogue (own TMEM rows), which releases the accumulator by arriving on the LEADER's barrier.
+//   8 warps         : 0 weight producer, 1 and 7 MMA issuers (1 also owns the TMEM allocation), 2-5 epilogue, 6 patch producer.
+//
+// Per-launch variations, all decided on the host (conv_pair_plan): tile classes and orientations (QProb), 16 x 8 tiles and
+// a 64-wide N tile for launches that fill few SMs, K chunks that are skipped or multiplied at half the N extent (the
+// wide-pixel form of conv1_2, net.cu), a weight set that stays in shared memory for the whole kernel (bres).
 #include "opb_common.cuh"
 #include "tc_ptx.cuh"
 #include <cstdlib>
