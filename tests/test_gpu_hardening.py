@@ -210,3 +210,9 @@ def test_fuzz_random_sizes_and_scales():
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "tools", "fuzz_body.py"), "10", "5"], cwd=root,
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "10 cases, 0 mismatches" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_graft_entry_smoke():
+    """The driver's smoke check (one small Body and Hand call against the oracle) stays green with the rest."""
+    import __graft_entry__ as entry
+    entry.smoke()
