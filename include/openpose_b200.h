@@ -220,6 +220,16 @@ int opb_conv2d(opb_context* ctx, const void* dev_in_bf16, int n, int h, int w, i
  * units of column PAIRS), b_wide [128].  Lets a CPU test prove the re-described layer equals the original one.        */
 int opb_wide_pool_weights(const float* weight, const float* bias, unsigned short* w_wide, float* b_wide);
 
+/* Host only (no device call): the resampling tables the library builds on the host and its kernels apply.
+ * opb_debug_resize_taps: cv2's INTER_CUBIC taps for one axis (first tap index, may lie outside the source: taps are
+ *   clamped when used; 4 float32 coefficients per destination index) -- src/body.py:38,55,57.
+ * opb_debug_composite_taps: the per-axis operator of "x8 cubic upsample, crop to n_resized, cubic resize to n_orig"
+ *   (src/body.py:55-57) as first source index + 6 float32 weights per destination index.
+ * opb_debug_resize_dsize: cv2's destination size for a scale factor (round half to even).                            */
+int opb_debug_resize_taps(int src, int dst, double scale, int* first, float* coef4);
+int opb_debug_composite_taps(int n_net, int n_resized, int n_orig, int* first, float* w6);
+int opb_debug_resize_dsize(int n, double f);
+
 /* Host only (no device call): the tile list of the CTA-pair convolution kernel for one problem of n images of h x w
  * pixels, exactly as the kernel decodes it -- 8 ints per (pair, cluster rank): image, x0, y0, n0, real (0 = padding tile,
  * computed but never stored), halves (bit h: 128-pixel half h holds pixels), vsplit (0 = halves side by side 8 x 16,

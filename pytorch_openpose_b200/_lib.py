@@ -77,6 +77,9 @@ SIGNATURES = {
                                    POINTER(c_int)]),
     "opb_smooth_debug": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
     "opb_wide_pool_weights": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "opb_debug_resize_taps": (c_int, [c_int, c_int, ctypes.c_double, c_void_p, c_void_p]),
+    "opb_debug_composite_taps": (c_int, [c_int, c_int, c_int, c_void_p, c_void_p]),
+    "opb_debug_resize_dsize": (c_int, [c_int, ctypes.c_double]),
     "opb_debug_pair_tiles": (c_int, [c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "opb_conv2d": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int,
                            c_int, c_int, c_void_p, c_int]),

@@ -1702,6 +1702,29 @@ int opb_debug_pair_tiles(int n, int h, int w, int n_tiles_n, int small, int* out
     });
 }
 
+int opb_debug_resize_taps(int src, int dst, double scale, int* first, float* coef4) {
+    return guarded([&] {
+        OPB_REQUIRE(first && coef4 && src >= 1 && dst >= 1, "opb_debug_resize_taps: bad argument");
+        const CubicTaps t = cubic_taps(src, dst, scale);
+        memcpy(first, t.first.data(), sizeof(int) * dst);
+        memcpy(coef4, t.coef.data(), sizeof(float) * 4 * dst);
+    });
+}
+
+int opb_debug_composite_taps(int n_net, int n_resized, int n_orig, int* first, float* w6) {
+    return guarded([&] {
+        OPB_REQUIRE(first && w6 && n_net >= 1 && n_resized >= 1 && n_resized <= 8 * n_net && n_orig >= 1,
+                    "opb_debug_composite_taps: bad argument");
+        std::vector<int> f;
+        std::vector<float> w;
+        composite_taps(n_net, n_resized, n_orig, f, w);
+        memcpy(first, f.data(), sizeof(int) * n_orig);
+        memcpy(w6, w.data(), sizeof(float) * 6 * n_orig);
+    });
+}
+
+int opb_debug_resize_dsize(int n, double f) { return resize_dsize(n, f); }
+
 int opb_wide_pool_weights(const float* weight, const float* bias, unsigned short* w_wide, float* b_wide) {
     return guarded([&] {
         OPB_REQUIRE(weight && bias && w_wide && b_wide, "opb_wide_pool_weights: null argument");

@@ -141,3 +141,50 @@ def test_conv_pair_tiling_covers_every_pixel_once():
 @given(st.integers(1, 9), st.integers(1, 200), st.integers(1, 200), st.integers(1, 4), st.booleans())
 def test_conv_pair_tiling_property(n, h, w, n_tiles_n, small):
     _check_tiling(n, h, w, n_tiles_n, int(small))
+
+
+def _lib_resize_taps(src, dst, scale):
+    from pytorch_openpose_b200 import _lib
+    first = np.zeros(dst, dtype=np.int32)
+    coef = np.zeros((dst, 4), dtype=np.float32)
+    _lib.check(_lib.lib().opb_debug_resize_taps(src, dst, float(scale), first.ctypes.data, coef.ctypes.data))
+    return first, coef
+
+
+@settings(max_examples=60, deadline=None)
+@given(src=st.integers(1, 1500), f=st.floats(0.05, 9.0))
+def test_library_cubic_taps_equal_the_oracles_bit_for_bit(src, f):
+    """The tables the kernels apply are built by host code of the .so; they must be the oracle's restatement of cv2's
+    float32 tap arithmetic exactly (the oracle itself is pinned against cv2 in test_oracle_golden / test_properties)."""
+    from pytorch_openpose_b200 import _lib
+    dst = O.resize_dsize(src, f)
+    assert _lib.lib().opb_debug_resize_dsize(src, float(f)) == dst
+    if dst < 1:
+        return
+    first, coef = _lib_resize_taps(src, dst, 1.0 / f)
+    ofirst, ocoef = O.cubic_taps(src, dst, 1.0 / f)
+    assert np.array_equal(first, ofirst)
+    assert np.array_equal(coef.view(np.uint32), np.asarray(ocoef, dtype=np.float32).view(np.uint32))
+
+
+@settings(max_examples=60, deadline=None)
+@given(n_net=st.integers(1, 170), crop=st.integers(0, 7), orig=st.integers(1, 1400))
+def test_library_composite_operator_equals_the_oracles(n_net, crop, orig):
+    """x8 cubic upsample -> crop -> cubic resize as ONE banded operator per axis (what the fused peak kernel, the
+    materialiser and the PAF sampler evaluate): equal to the product of the oracle's two cubic matrices."""
+    from pytorch_openpose_b200 import _lib
+    n_resized = 8 * n_net - crop
+    if n_resized < 1:
+        return
+    # the network sees the frame resized by 184..736 / H: the way back is a resize by 0.25..4 (src/body.py:57)
+    n_orig = min(max(orig, (n_resized + 3) // 4), 4 * n_resized)
+    first = np.zeros(n_orig, dtype=np.int32)
+    w6 = np.zeros((n_orig, 6), dtype=np.float32)
+    _lib.check(_lib.lib().opb_debug_composite_taps(n_net, n_resized, n_orig, first.ctypes.data, w6.ctypes.data))
+    dense = np.zeros((n_orig, n_net + 6))
+    for o in range(n_orig):
+        dense[o, first[o]:first[o] + 6] = w6[o]
+    assert not dense[:, n_net:].any(), "weights beyond the last net column"
+    M = O.composite_upsample_matrix(n_net, n_resized, n_orig)
+    assert np.abs(dense[:, :n_net] - M).max() <= 2e-7                     # the library rounds the float64 products to float32
+    assert np.abs(dense[:, :n_net].sum(1) - 1).max() < 1e-5
